@@ -1,0 +1,152 @@
+/*
+ * pbllm.h -- C ABI of libpbllm.so: B200 (sm_100a) partially-binarized linear forward.
+ *
+ * Drop-in boundary for the ONE hot path of hahnyuan/PB-LLM: the forward of
+ *   quant/quantizer.py:75-86      BinaryLinear          (and FdaBinaryLinear  :112-128, same forward)
+ *   quant/quantizer.py:172-193    XnorBinaryLinear      (and IrBinaryLinear   :89-109,  same forward)
+ *   quant/outlier_quantizer.py:33-123  BinaryXnorExceptOutliersLinear (+ ...Hessian :126-143)
+ *   gptq_pb/gptq.py:180-184       the fp16 nn.Linear that GPTQ-PB writes (format a10)
+ * all of which end in  F.linear(x, w_sim, bias)  over a re-materialised dense w_sim
+ * (quant/quantizer.py:86,193; quant/outlier_quantizer.py:105).  This library evaluates the same
+ * y = x . w_sim^T + bias from a packed form of w_sim (1-bit sign plane + salient bitmap + packed
+ * salient values + per-(row,group) {lo,hi}); unpack(pack(w_sim)) == w_sim bit-exactly.
+ *
+ * Conventions: plain pointers and sizes, no torch types, no exceptions across the ABI.
+ * Every entry point returns PBL_OK (0) or a negative pbl_status; pbl_last_error() gives the
+ * thread-local message.  Device pointers are borrowed (owned by the caller's allocator);
+ * kernels run on the caller's stream with no internal synchronisation (CUDA-graph capturable).
+ * There is NO CPU fallback: on a machine without an sm_100 device every compute entry point
+ * returns PBL_ERR_NO_DEVICE / PBL_ERR_ARCH.
+ */
+#ifndef PBLLM_H_
+#define PBLLM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBL_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PBL_API __attribute__((visibility("default")))
+#else
+#define PBL_API
+#endif
+
+typedef enum {
+    PBL_OK = 0,
+    PBL_ERR_NULL = -1,      /* null pointer argument */
+    PBL_ERR_DTYPE = -2,     /* dtype not one of pbl_dtype / not supported by this path */
+    PBL_ERR_SHAPE = -3,     /* bad N/K/M/groupsize/leading dimension */
+    PBL_ERR_NO_DEVICE = -4, /* no CUDA device / driver */
+    PBL_ERR_ARCH = -5,      /* device is not sm_100 (B200) */
+    PBL_ERR_CUDA = -6,      /* a CUDA runtime call failed; message carries cudaGetErrorString */
+    PBL_ERR_ALIGN = -7,     /* pointer not aligned as required (16 B for x, y, packed buffers) */
+    PBL_ERR_UNSUPPORTED = -8
+} pbl_status;
+
+/* dtype of activations x, outputs y and packed salient values (the reference requires
+ * x.dtype == weight.dtype, SURVEY.md 8b "Call"). */
+typedef enum { PBL_F16 = 0, PBL_BF16 = 1, PBL_F32 = 2 } pbl_dtype;
+
+/* Packed layout geometry: plane tiles are PBL_TILE_ROWS output rows x PBL_TILE_COLS input
+ * columns; rows/cols are padded to whole tiles inside the packed buffers only. */
+#define PBL_TILE_ROWS 128
+#define PBL_TILE_COLS 64
+#define PBL_RG_ROWS 32 /* rows per value row-group (one warp) */
+
+typedef struct {
+    int64_t n_pad, k_pad;       /* N, K rounded up to whole tiles */
+    int64_t tiles_r, tiles_c;   /* n_pad/128, k_pad/64 */
+    int64_t groups;             /* ceil(K / groupsize) */
+    size_t planes_bytes;        /* u32 [tiles_r][tiles_c][128][4] = {sign0,sign1,sal0,sal1} per row */
+    size_t vptr_bytes;          /* u32 [tiles_r*tiles_c*4 + 1] value offsets per (tile, row-group) */
+    size_t affine_bytes;        /* float2 {lo,hi} [n_pad][groups] */
+    size_t vals_elem_bytes;     /* sizeof(dtype); vals buffer = (nnz + 8) * vals_elem_bytes */
+} pbl_sizes;
+
+/* Host-only. groupsize <= 0 or >= K means one group per row; otherwise it must be a multiple
+ * of PBL_TILE_COLS (GPTQ-PB requires groupsize % 128 == 0, gptq_pb/gptq.py:102). */
+PBL_API int pbl_pack_sizes(int64_t N, int64_t K, int64_t groupsize, int dtype, pbl_sizes* out);
+
+/* ---- packing (one-time; replaces the per-forward re-binarisation of quant/quantizer.py:183-188
+ *      and quant/outlier_quantizer.py:94-98) -------------------------------------------------- */
+
+/* {lo,hi}[row][group] = {min,max} of w_sim over the binarized positions of the group
+ * (all positions if low_mask == NULL).  w_sim: device dense [N][ldw] of `dtype`;
+ * low_mask: device uint8/bool [N][K], nonzero = binarized (the GPTQ-PB mask-file convention,
+ * gptq_pb/gptq.py:92,99; the complement of outlier_mask, quant/outlier_quantizer.py:138). */
+PBL_API int pbl_pack_affine(const void* w_sim, int64_t ldw, const uint8_t* low_mask, int64_t N, int64_t K,
+                    int64_t groupsize, int dtype, void* affine_out, void* stream);
+
+/* Pass 1: writes the planes and the per-(tile,row-group) salient counts, then scans them in
+ * place into offsets; vptr_out[last] = nnz (read it back to size `vals`).  An element is
+ * binarized iff (low_mask == NULL || low_mask[i][j]) && (w == lo || w == hi); everything else
+ * (salient weights, sign(0) zeros, any third value) is salient and stored exactly. */
+PBL_API int pbl_pack_planes(const void* w_sim, int64_t ldw, const uint8_t* low_mask, const void* affine, int64_t N,
+                    int64_t K, int64_t groupsize, int dtype, void* planes_out, void* vptr_out, void* stream);
+
+/* Pass 2: gathers the salient values (tile-major, row-group, row, column order). */
+PBL_API int pbl_pack_vals(const void* w_sim, int64_t ldw, const void* planes, const void* vptr, int64_t N, int64_t K,
+                  int dtype, void* vals_out, void* stream);
+
+/* ---- layer handle ------------------------------------------------------------------------ */
+
+typedef struct {
+    int64_t N, K;        /* out_features, in_features of the replaced nn.Linear */
+    int64_t groupsize;   /* as given to pbl_pack_sizes */
+    int32_t dtype;       /* pbl_dtype */
+    int32_t reserved;
+    const void* planes;  /* device, 16 B aligned */
+    const void* vptr;    /* device */
+    const void* vals;    /* device, dtype, 16 B aligned, >= nnz + 8 elements */
+    const void* affine;  /* device float2 [n_pad][groups] */
+    const void* bias;    /* device float32 [N] or NULL (bias added inside, as F.linear does) */
+} pbl_layer_desc;
+
+typedef struct pbl_layer pbl_layer; /* opaque; borrows the descriptor's device pointers */
+
+PBL_API int pbl_layer_create(const pbl_layer_desc* desc, pbl_layer** out);
+PBL_API void pbl_layer_destroy(pbl_layer* layer);
+
+/* Reconstruct the dense w_sim [N][ldw] (dtype) from the packed form -- the pack invariant
+ * check and the backing of the modules' `.weight` / to_regular_linear()
+ * (quant/outlier_quantizer.py:108-114). */
+PBL_API int pbl_unpack(const pbl_layer* layer, void* w_out, int64_t ldw, void* stream);
+
+/* ---- the hot path ------------------------------------------------------------------------ */
+
+/* y[m][i] = sum_j x[m][j] * w_sim[i][j] + bias[i]   (fp32 accumulation, y rounded to dtype)
+ * Replaces F.linear(x, w_sim, bias) at quant/quantizer.py:86,193 and
+ * quant/outlier_quantizer.py:105.  x: device [M][ldx], y: device [M][ldy] (row-major, dtype).
+ * M = product of the leading dims of the reference's x[..., K].  M == 0 is a no-op. */
+PBL_API int pbl_linear_forward(const pbl_layer* layer, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M,
+                       void* stream);
+
+/* Same call with HOST buffers (the reference-facing end-to-end form, used for bench.py's
+ * `e2e`): copies x host->device, runs the kernel, copies y device->host on `stream` and
+ * synchronises it.  x_host/y_host should be pinned for full PCIe rate.  `workspace` is a
+ * device buffer of at least pbl_forward_host_workspace(layer, M) bytes. */
+PBL_API size_t pbl_forward_host_workspace(const pbl_layer* layer, int64_t M);
+PBL_API int pbl_linear_forward_host(const pbl_layer* layer, const void* x_host, void* y_host, int64_t M, void* workspace,
+                            void* stream);
+
+/* Which kernel pbl_linear_forward would launch for this (layer, M): 0 = CUDA-core bit-plane
+ * GEMV/skinny kernel, 1 = tcgen05 bit-plane GEMM.  PBL_FORCE_KERNEL=0|1 overrides (tests). */
+PBL_API int pbl_select_kernel(const pbl_layer* layer, int64_t M);
+
+/* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */
+PBL_API int64_t pbl_launch_count(void);
+
+PBL_API const char* pbl_last_error(void);
+PBL_API int pbl_abi_version(void);
+/* 0 when an sm_100 device is usable, else PBL_ERR_NO_DEVICE / PBL_ERR_ARCH. */
+PBL_API int pbl_device_check(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBLLM_H_ */

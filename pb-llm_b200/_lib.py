@@ -1,0 +1,88 @@
+"""ctypes binding of libpbllm.so (include/pbllm.h). Fails loudly if the library is missing or
+cannot run: there is no Python/CPU fallback for any compute entry point."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+PBL_F16, PBL_BF16, PBL_F32 = 0, 1, 2
+TILE_ROWS, TILE_COLS, RG_ROWS = 128, 64, 32
+
+
+class PblSizes(C.Structure):
+    _fields_ = [("n_pad", C.c_int64), ("k_pad", C.c_int64), ("tiles_r", C.c_int64), ("tiles_c", C.c_int64),
+                ("groups", C.c_int64), ("planes_bytes", C.c_size_t), ("vptr_bytes", C.c_size_t),
+                ("affine_bytes", C.c_size_t), ("vals_elem_bytes", C.c_size_t)]
+
+
+class PblLayerDesc(C.Structure):
+    _fields_ = [("N", C.c_int64), ("K", C.c_int64), ("groupsize", C.c_int64), ("dtype", C.c_int32),
+                ("reserved", C.c_int32), ("planes", C.c_void_p), ("vptr", C.c_void_p), ("vals", C.c_void_p),
+                ("affine", C.c_void_p), ("bias", C.c_void_p)]
+
+
+# name -> (restype, argtypes): every symbol include/pbllm.h declares
+SYMBOLS = {
+    "pbl_pack_sizes": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(PblSizes)]),
+    "pbl_pack_affine": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                  C.c_void_p, C.c_void_p]),
+    "pbl_pack_planes": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pbl_pack_vals": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
+                                C.c_void_p, C.c_void_p]),
+    "pbl_layer_create": (C.c_int, [C.POINTER(PblLayerDesc), C.POINTER(C.c_void_p)]),
+    "pbl_layer_destroy": (None, [C.c_void_p]),
+    "pbl_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pbl_linear_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+                                     C.c_void_p]),
+    "pbl_forward_host_workspace": (C.c_size_t, [C.c_void_p, C.c_int64]),
+    "pbl_linear_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "pbl_select_kernel": (C.c_int, [C.c_void_p, C.c_int64]),
+    "pbl_launch_count": (C.c_int64, []),
+    "pbl_last_error": (C.c_char_p, []),
+    "pbl_abi_version": (C.c_int, []),
+    "pbl_device_check": (C.c_int, []),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load libpbllm.so (building it with nvcc if the sources are newer). Raises RuntimeError
+    if it cannot be had -- the package is unusable without its CUDA library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if _build.needs_build():
+        try:
+            path = _build.build()
+        except Exception as e:  # noqa: BLE001
+            if not os.path.exists(path):
+                raise RuntimeError(f"libpbllm.so is missing and could not be built: {e}") from e
+    try:
+        lib = C.CDLL(path)
+    except OSError as e:
+        raise RuntimeError(f"cannot load {path}: {e}; pb-llm_b200 has no CPU fallback") from e
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if lib.pbl_abi_version() != 1:
+        raise RuntimeError("libpbllm.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().pbl_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = "libpbllm"):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (status {rc}): {last_error()}")

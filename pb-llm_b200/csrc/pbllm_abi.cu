@@ -1,0 +1,244 @@
+// C ABI of libpbllm.so (see include/pbllm.h). Host-side glue only: argument checking, the
+// opaque layer handle, kernel selection, thread-local error string. No torch types, no
+// exceptions across the boundary, no CPU fallback.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "pbllm_common.cuh"
+
+namespace pbl {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return PBL_OK;
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return PBL_ERR_CUDA;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static int device_check_impl() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        set_error("no CUDA device available (%s); libpbllm has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return PBL_ERR_NO_DEVICE;
+    }
+    int dev = 0, major = 0, minor = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed"); return PBL_ERR_NO_DEVICE; }
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    if (major != 10) {
+        set_error("device %d is sm_%d%d; libpbllm is built for sm_100a (B200) only", dev, major, minor);
+        return PBL_ERR_ARCH;
+    }
+    return PBL_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static bool valid_dtype(int d) { return d == PBL_F16 || d == PBL_BF16 || d == PBL_F32; }
+static size_t dtype_size(int d) { return d == PBL_F32 ? 4 : 2; }
+
+static int sizes_impl(int64_t N, int64_t K, int64_t gs, int dtype, pbl_sizes* out) {
+    if (!out) { set_error("pbl_pack_sizes: out is NULL"); return PBL_ERR_NULL; }
+    if (!valid_dtype(dtype)) { set_error("pbl_pack_sizes: bad dtype %d", dtype); return PBL_ERR_DTYPE; }
+    if (N <= 0 || K <= 0) { set_error("pbl_pack_sizes: N=%lld K=%lld must be positive", (long long)N, (long long)K); return PBL_ERR_SHAPE; }
+    if (gs <= 0 || gs >= K) gs = K;
+    else if (gs % kTileCols != 0) {
+        set_error("groupsize %lld must be a multiple of %d (or cover the whole row)", (long long)gs, kTileCols);
+        return PBL_ERR_SHAPE;
+    }
+    pbl_sizes s;
+    s.n_pad = (N + kTileRows - 1) / kTileRows * kTileRows;
+    s.k_pad = (K + kTileCols - 1) / kTileCols * kTileCols;
+    s.tiles_r = s.n_pad / kTileRows;
+    s.tiles_c = s.k_pad / kTileCols;
+    s.groups = (K + gs - 1) / gs;
+    if (s.tiles_r * s.tiles_c * kRgPerTile >= (int64_t)1 << 31 || N * K >= (int64_t)1 << 32) {
+        set_error("layer too large for 32-bit value offsets"); return PBL_ERR_SHAPE;
+    }
+    s.planes_bytes = (size_t)(s.tiles_r * s.tiles_c * kTileRows) * sizeof(uint4);
+    s.vptr_bytes = (size_t)(s.tiles_r * s.tiles_c * kRgPerTile + 1) * sizeof(uint32_t);
+    s.affine_bytes = (size_t)(s.n_pad * s.groups) * sizeof(float2);
+    s.vals_elem_bytes = dtype_size(dtype);
+    *out = s;
+    return PBL_OK;
+}
+
+}  // namespace pbl
+
+using namespace pbl;
+
+extern "C" {
+
+int pbl_abi_version(void) { return PBL_ABI_VERSION; }
+const char* pbl_last_error(void) { return g_err; }
+int64_t pbl_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int pbl_device_check(void) { return device_check_impl(); }
+
+int pbl_pack_sizes(int64_t N, int64_t K, int64_t groupsize, int dtype, pbl_sizes* out) {
+    return sizes_impl(N, K, groupsize, dtype, out);
+}
+
+int pbl_pack_affine(const void* w_sim, int64_t ldw, const uint8_t* low_mask, int64_t N, int64_t K,
+                    int64_t groupsize, int dtype, void* affine_out, void* stream) {
+    pbl_sizes sz;
+    int rc = sizes_impl(N, K, groupsize, dtype, &sz);
+    if (rc) return rc;
+    if (!w_sim || !affine_out) { set_error("pbl_pack_affine: null pointer"); return PBL_ERR_NULL; }
+    if (ldw < K) { set_error("pbl_pack_affine: ldw %lld < K %lld", (long long)ldw, (long long)K); return PBL_ERR_SHAPE; }
+    if ((rc = device_check_impl())) return rc;
+    const int64_t gs = (groupsize <= 0 || groupsize >= K) ? K : groupsize;
+    return launch_pack_affine(w_sim, ldw, low_mask, N, K, gs, dtype, (float2*)affine_out, sz.n_pad, sz.groups,
+                              (cudaStream_t)stream);
+}
+
+int pbl_pack_planes(const void* w_sim, int64_t ldw, const uint8_t* low_mask, const void* affine, int64_t N,
+                    int64_t K, int64_t groupsize, int dtype, void* planes_out, void* vptr_out, void* stream) {
+    pbl_sizes sz;
+    int rc = sizes_impl(N, K, groupsize, dtype, &sz);
+    if (rc) return rc;
+    if (!w_sim || !affine || !planes_out || !vptr_out) { set_error("pbl_pack_planes: null pointer"); return PBL_ERR_NULL; }
+    if (ldw < K) { set_error("pbl_pack_planes: ldw %lld < K %lld", (long long)ldw, (long long)K); return PBL_ERR_SHAPE; }
+    if (!aligned16(planes_out)) { set_error("pbl_pack_planes: planes_out must be 16 B aligned"); return PBL_ERR_ALIGN; }
+    if ((rc = device_check_impl())) return rc;
+    const int64_t gs = (groupsize <= 0 || groupsize >= K) ? K : groupsize;
+    return launch_pack_planes(w_sim, ldw, low_mask, (const float2*)affine, N, K, gs, dtype, (uint4*)planes_out,
+                              (uint32_t*)vptr_out, sz, (cudaStream_t)stream);
+}
+
+int pbl_pack_vals(const void* w_sim, int64_t ldw, const void* planes, const void* vptr, int64_t N, int64_t K,
+                  int dtype, void* vals_out, void* stream) {
+    pbl_sizes sz;
+    int rc = sizes_impl(N, K, 0, dtype, &sz);
+    if (rc) return rc;
+    if (!w_sim || !planes || !vptr || !vals_out) { set_error("pbl_pack_vals: null pointer"); return PBL_ERR_NULL; }
+    if (ldw < K) { set_error("pbl_pack_vals: ldw %lld < K %lld", (long long)ldw, (long long)K); return PBL_ERR_SHAPE; }
+    if ((rc = device_check_impl())) return rc;
+    return launch_pack_vals(w_sim, ldw, (const uint4*)planes, (const uint32_t*)vptr, N, K, dtype, vals_out, sz,
+                            (cudaStream_t)stream);
+}
+
+int pbl_layer_create(const pbl_layer_desc* d, pbl_layer** out) {
+    if (!d || !out) { set_error("pbl_layer_create: null pointer"); return PBL_ERR_NULL; }
+    *out = nullptr;
+    pbl_sizes sz;
+    int rc = sizes_impl(d->N, d->K, d->groupsize, d->dtype, &sz);
+    if (rc) return rc;
+    if (!d->planes || !d->vptr || !d->vals || !d->affine) { set_error("pbl_layer_create: null packed buffer"); return PBL_ERR_NULL; }
+    if (!aligned16(d->planes) || !aligned16(d->vals)) { set_error("pbl_layer_create: planes/vals must be 16 B aligned"); return PBL_ERR_ALIGN; }
+    Layer* L = new (std::nothrow) Layer();
+    if (!L) { set_error("out of host memory"); return PBL_ERR_CUDA; }
+    L->N = d->N; L->K = d->K;
+    L->groupsize = (d->groupsize <= 0 || d->groupsize >= d->K) ? d->K : d->groupsize;
+    L->dtype = d->dtype;
+    L->n_pad = sz.n_pad; L->k_pad = sz.k_pad; L->tiles_r = sz.tiles_r; L->tiles_c = sz.tiles_c; L->groups = sz.groups;
+    L->tiles_per_group = (sz.groups == 1) ? (int)sz.tiles_c : (int)(L->groupsize / kTileCols);
+    L->planes = (const uint4*)d->planes; L->vptr = (const uint32_t*)d->vptr; L->vals = d->vals;
+    L->affine = (const float2*)d->affine; L->bias = (const float*)d->bias;
+    *out = reinterpret_cast<pbl_layer*>(L);
+    return PBL_OK;
+}
+
+void pbl_layer_destroy(pbl_layer* layer) { delete reinterpret_cast<Layer*>(layer); }
+
+int pbl_unpack(const pbl_layer* layer, void* w_out, int64_t ldw, void* stream) {
+    if (!layer || !w_out) { set_error("pbl_unpack: null pointer"); return PBL_ERR_NULL; }
+    const Layer& L = *reinterpret_cast<const Layer*>(layer);
+    if (ldw < L.K) { set_error("pbl_unpack: ldw < K"); return PBL_ERR_SHAPE; }
+    int rc = device_check_impl();
+    if (rc) return rc;
+    return launch_unpack(L, w_out, ldw, (cudaStream_t)stream);
+}
+
+static int forced_kernel() {
+    const char* e = getenv("PBL_FORCE_KERNEL");
+    if (!e || !*e) return -1;
+    return atoi(e);
+}
+
+static int gemv_max_m() {
+    const char* e = getenv("PBL_GEMV_MAX_M");
+    if (e && *e) return atoi(e);
+    return 8;
+}
+
+static int select_impl(const Layer& L, const void* x, int64_t ldx, const void* y, int64_t ldy, int64_t M) {
+    const bool tc_ok = gemm_tc_supported(L, x, ldx, y, ldy, M);
+    const int f = forced_kernel();
+    if (f == 0) return 0;
+    if (f == 1) return tc_ok ? 1 : -1;
+    if (!tc_ok) return 0;
+    return (M <= gemv_max_m()) ? 0 : 1;
+}
+
+int pbl_select_kernel(const pbl_layer* layer, int64_t M) {
+    if (!layer) { set_error("pbl_select_kernel: null layer"); return PBL_ERR_NULL; }
+    const Layer& L = *reinterpret_cast<const Layer*>(layer);
+    return select_impl(L, nullptr, L.K, nullptr, L.N, M);
+}
+
+int pbl_linear_forward(const pbl_layer* layer, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M,
+                       void* stream) {
+    if (!layer) { set_error("pbl_linear_forward: null layer"); return PBL_ERR_NULL; }
+    const Layer& L = *reinterpret_cast<const Layer*>(layer);
+    if (M < 0) { set_error("pbl_linear_forward: M=%lld < 0", (long long)M); return PBL_ERR_SHAPE; }
+    if (M == 0) return PBL_OK;
+    if (!x || !y) { set_error("pbl_linear_forward: null x or y"); return PBL_ERR_NULL; }
+    if (ldx < L.K || ldy < L.N) {
+        set_error("pbl_linear_forward: ldx=%lld (K=%lld) or ldy=%lld (N=%lld) too small", (long long)ldx, (long long)L.K,
+                  (long long)ldy, (long long)L.N);
+        return PBL_ERR_SHAPE;
+    }
+    int rc = device_check_impl();
+    if (rc) return rc;
+    const int k = select_impl(L, x, ldx, y, ldy, M);
+    if (k < 0) { set_error("PBL_FORCE_KERNEL=1 but the tcgen05 path does not support this call"); return PBL_ERR_UNSUPPORTED; }
+    if (k == 1) return launch_gemm_tc(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
+    return launch_gemv(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
+}
+
+size_t pbl_forward_host_workspace(const pbl_layer* layer, int64_t M) {
+    if (!layer || M <= 0) return 0;
+    const Layer& L = *reinterpret_cast<const Layer*>(layer);
+    const size_t es = dtype_size(L.dtype);
+    const size_t xb = ((size_t)M * (size_t)L.K * es + 255) / 256 * 256;
+    const size_t yb = ((size_t)M * (size_t)L.N * es + 255) / 256 * 256;
+    return xb + yb;
+}
+
+int pbl_linear_forward_host(const pbl_layer* layer, const void* x_host, void* y_host, int64_t M, void* workspace,
+                            void* stream) {
+    if (!layer) { set_error("pbl_linear_forward_host: null layer"); return PBL_ERR_NULL; }
+    if (M == 0) return PBL_OK;
+    if (!x_host || !y_host || !workspace) { set_error("pbl_linear_forward_host: null pointer"); return PBL_ERR_NULL; }
+    const Layer& L = *reinterpret_cast<const Layer*>(layer);
+    int rc = device_check_impl();
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t es = dtype_size(L.dtype);
+    const size_t xb = (size_t)M * (size_t)L.K * es, yb = (size_t)M * (size_t)L.N * es;
+    char* xd = (char*)workspace;
+    char* yd = xd + (xb + 255) / 256 * 256;
+    if ((rc = check_cuda(cudaMemcpyAsync(xd, x_host, xb, cudaMemcpyHostToDevice, s), "H2D x"))) return rc;
+    if ((rc = pbl_linear_forward(layer, xd, L.K, yd, L.N, M, stream))) return rc;
+    if ((rc = check_cuda(cudaMemcpyAsync(y_host, yd, yb, cudaMemcpyDeviceToHost, s), "D2H y"))) return rc;
+    return check_cuda(cudaStreamSynchronize(s), "stream sync");
+}
+
+}  // extern "C"

@@ -1,0 +1,165 @@
+"""PackedLinear: device buffers of one packed partially-binarized linear + its pbl_layer handle.
+
+torch is used for device memory and the current stream only; all arithmetic on the packed form
+happens inside libpbllm.so (include/pbllm.h)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float16: _lib.PBL_F16, torch.bfloat16: _lib.PBL_BF16, torch.float32: _lib.PBL_F32}
+
+
+def _stream(dev) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def pack_sizes(N: int, K: int, groupsize: int, dtype: torch.dtype) -> _lib.PblSizes:
+    sz = _lib.PblSizes()
+    _lib.check(_lib.load().pbl_pack_sizes(N, K, groupsize, _DT[dtype], C.byref(sz)), "pbl_pack_sizes")
+    return sz
+
+
+class PackedLinear:
+    """Packed form of a dense fake-quant weight w_sim [N, K] (the tensor the reference feeds to
+    F.linear: quant/quantizer.py:86,193; quant/outlier_quantizer.py:105)."""
+
+    def __init__(self):
+        self.handle = None
+
+    @classmethod
+    def from_dense(cls, w_sim: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                   low_mask: Optional[torch.Tensor] = None, groupsize: int = -1, verify: bool = False):
+        """w_sim: CUDA [N,K] fp16/bf16/fp32. low_mask: bool [N,K], True = binarized position
+        (the GPTQ-PB mask-file convention); None = every position may be binarized."""
+        if not w_sim.is_cuda:
+            raise RuntimeError("PackedLinear.from_dense needs a CUDA tensor: pb-llm_b200 has no CPU path")
+        if w_sim.dtype not in _DT:
+            raise RuntimeError(f"unsupported weight dtype {w_sim.dtype}")
+        if w_sim.dim() != 2:
+            raise RuntimeError("w_sim must be [out_features, in_features]")
+        lib = _lib.load()
+        dev = w_sim.device
+        w = w_sim.detach()
+        if w.stride(-1) != 1:
+            w = w.contiguous()
+        N, K = w.shape
+        self = cls()
+        self.N, self.K, self.dtype, self.device = N, K, w.dtype, dev
+        self.groupsize = K if (groupsize is None or groupsize <= 0 or groupsize >= K) else int(groupsize)
+        sz = pack_sizes(N, K, self.groupsize, w.dtype)
+        self.sizes = sz
+        mptr = None
+        if low_mask is not None:
+            if low_mask.shape != w.shape:
+                raise RuntimeError("low_mask shape must equal the weight shape")
+            lm = low_mask.to(device=dev).contiguous()
+            lm = lm.view(torch.uint8) if lm.dtype == torch.bool else (lm != 0).view(torch.uint8)
+            mptr = C.c_void_p(lm.data_ptr())
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            self.affine = torch.empty(sz.n_pad * sz.groups * 2, dtype=torch.float32, device=dev)
+            self.planes = torch.empty(sz.planes_bytes // 4, dtype=torch.int32, device=dev)
+            self.vptr = torch.empty(sz.vptr_bytes // 4, dtype=torch.int32, device=dev)
+            wp, ldw, dt = C.c_void_p(w.data_ptr()), w.stride(0), _DT[w.dtype]
+            _lib.check(lib.pbl_pack_affine(wp, ldw, mptr, N, K, self.groupsize, dt, C.c_void_p(self.affine.data_ptr()), st),
+                       "pbl_pack_affine")
+            _lib.check(lib.pbl_pack_planes(wp, ldw, mptr, C.c_void_p(self.affine.data_ptr()), N, K, self.groupsize, dt,
+                                           C.c_void_p(self.planes.data_ptr()), C.c_void_p(self.vptr.data_ptr()), st),
+                       "pbl_pack_planes")
+            self.nnz = int(self.vptr[-1].item()) & 0xFFFFFFFF
+            self.vals = torch.zeros(self.nnz + 8, dtype=w.dtype, device=dev)
+            _lib.check(lib.pbl_pack_vals(wp, ldw, C.c_void_p(self.planes.data_ptr()), C.c_void_p(self.vptr.data_ptr()),
+                                         N, K, dt, C.c_void_p(self.vals.data_ptr()), st), "pbl_pack_vals")
+            self.bias = None if bias is None else bias.detach().to(device=dev, dtype=torch.float32).contiguous()
+            self._create()
+            if verify:
+                back = self.unpack()
+                if not torch.equal(back, w):
+                    raise RuntimeError("pack invariant violated: unpack(pack(w_sim)) != w_sim")
+        return self
+
+    @classmethod
+    def from_buffers(cls, N, K, groupsize, dtype, planes, vptr, vals, affine, bias=None):
+        """Re-create from previously packed device buffers (packed checkpoints / row shards)."""
+        self = cls()
+        self.N, self.K, self.dtype, self.device = int(N), int(K), dtype, planes.device
+        self.groupsize = K if groupsize <= 0 or groupsize >= K else int(groupsize)
+        self.sizes = pack_sizes(N, K, self.groupsize, dtype)
+        self.planes, self.vptr, self.vals, self.affine = planes, vptr, vals, affine
+        self.bias = None if bias is None else bias.to(device=planes.device, dtype=torch.float32).contiguous()
+        self.nnz = int(vptr[-1].item()) & 0xFFFFFFFF
+        self._create()
+        return self
+
+    def _create(self):
+        d = _lib.PblLayerDesc(self.N, self.K, self.groupsize, _DT[self.dtype], 0, self.planes.data_ptr(),
+                              self.vptr.data_ptr(), self.vals.data_ptr(), self.affine.data_ptr(),
+                              0 if self.bias is None else self.bias.data_ptr())
+        h = C.c_void_p()
+        _lib.check(_lib.load().pbl_layer_create(C.byref(d), C.byref(h)), "pbl_layer_create")
+        self.handle = h
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h is not None and _lib._lib is not None:
+            _lib._lib.pbl_layer_destroy(h)
+
+    # -- the hot path ----------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """y = x @ w_sim.T + bias through pbl_linear_forward on the current stream."""
+        if not x.is_cuda:
+            raise RuntimeError("pb-llm_b200 forward needs CUDA activations (no CPU fallback)")
+        if x.dtype != self.dtype:  # the reference raises on mixed dtypes too (SURVEY 8b "Call")
+            raise RuntimeError(f"activation dtype {x.dtype} != packed weight dtype {self.dtype}")
+        if x.shape[-1] != self.K:
+            raise RuntimeError(f"last dim of x is {x.shape[-1]}, expected in_features={self.K}")
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, self.K)
+        if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < self.K):
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        y = out if out is not None else torch.empty((M, self.N), dtype=self.dtype, device=x.device)
+        if M:
+            with torch.cuda.device(x.device):
+                rc = _lib.load().pbl_linear_forward(self.handle, C.c_void_p(x2.data_ptr()), x2.stride(0) if M > 1 else self.K,
+                                                    C.c_void_p(y.data_ptr()), y.stride(0), M, _stream(x.device))
+            _lib.check(rc, "pbl_linear_forward")
+        return y.view(*lead, self.N) if out is None else y
+
+    def forward_host(self, x_host: torch.Tensor, y_host: torch.Tensor, workspace: torch.Tensor):
+        """End-to-end form with HOST buffers (pbl_linear_forward_host): H2D, kernel, D2H, sync."""
+        M = x_host.numel() // self.K
+        rc = _lib.load().pbl_linear_forward_host(self.handle, C.c_void_p(x_host.data_ptr()), C.c_void_p(y_host.data_ptr()),
+                                                 M, C.c_void_p(workspace.data_ptr()), _stream(self.device))
+        _lib.check(rc, "pbl_linear_forward_host")
+
+    def host_workspace_bytes(self, M: int) -> int:
+        return int(_lib.load().pbl_forward_host_workspace(self.handle, M))
+
+    def select_kernel(self, M: int) -> int:
+        return int(_lib.load().pbl_select_kernel(self.handle, M))
+
+    def unpack(self) -> torch.Tensor:
+        """Dense w_sim [N,K] reconstructed bit-exactly from the packed form."""
+        w = torch.empty((self.N, self.K), dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().pbl_unpack(self.handle, C.c_void_p(w.data_ptr()), self.K, _stream(self.device)),
+                       "pbl_unpack")
+        return w
+
+    # -- accounting --------------------------------------------------------------------------
+    def packed_bytes(self) -> int:
+        es = 4 if self.dtype == torch.float32 else 2
+        return int(self.sizes.planes_bytes + self.sizes.vptr_bytes + self.sizes.affine_bytes + self.nnz * es
+                   + (0 if self.bias is None else 4 * self.N))
+
+    def bits_per_weight(self) -> float:
+        return 8.0 * self.packed_bytes() / (self.N * self.K)
+
+    def buffers(self) -> dict:
+        return dict(planes=self.planes, vptr=self.vptr, vals=self.vals, affine=self.affine, bias=self.bias)

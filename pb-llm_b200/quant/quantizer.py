@@ -1,0 +1,163 @@
+"""Packed drop-ins for quant/quantizer.py of the reference.
+
+Each class keeps the reference's constructor signature `Cls(weight, bias)`, its `weight` /
+`bias` parameters (fp32, reference quantizer.py:78-80,175-177), `BinaryInterface`, and the
+value of `forward(x)`; what changes is HOW forward is evaluated: the effective weight w_sim is
+built ONCE (with the same torch ops, in the same order and dtype as the reference, so the sign
+bits and scales are the reference's own -- SURVEY.md fact 6), packed by libpbllm.so, and every
+forward is a single pbl_linear_forward call. Inference only: the STE backward passes
+(reference quantizer.py:8-67) are out of scope."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from ..packing import PackedLinear
+
+
+class BinaryInterface:
+    """Reference quantizer.py:70-72."""
+
+    def get_save_weight_dict(self):
+        return {"weight": self.weight.data.half().cpu(), "bias": self.bias}
+
+
+class _PackedBase(nn.Module, BinaryInterface):
+    """Shared lazy-pack machinery. Subclasses implement `_effective_weight()` returning
+    (w_sim [N,K] on the weight's device, low_mask or None, groupsize)."""
+
+    def _init_params(self, weight, bias, cast_fp32: bool):
+        w = weight.data if isinstance(weight, nn.Parameter) else weight.detach()
+        self.weight = nn.Parameter(w.to(torch.float32) if cast_fp32 else w, requires_grad=False)
+        if bias is not None:
+            b = bias.data if isinstance(bias, nn.Parameter) else bias.detach()
+            self.bias = nn.Parameter(b.to(torch.float32) if cast_fp32 else b, requires_grad=False)
+        else:
+            self.bias = None
+        self._packed: Optional[PackedLinear] = None
+        self._packed_key = None
+        self._latent_dropped = False
+        self.global_name = None
+        self.out_features, self.in_features = w.shape
+
+    def _key(self):
+        w = self.weight
+        b = self.bias
+        return (w.data_ptr(), w._version, w.dtype, w.device, None if b is None else (b.data_ptr(), b._version))
+
+    def _effective_weight(self):
+        raise NotImplementedError
+
+    @torch.no_grad()
+    def pack(self, keep_latent: bool = True, verify: bool = False) -> PackedLinear:
+        """Build w_sim with the reference's arithmetic and pack it. keep_latent=False frees the
+        latent weight afterwards (`.weight` becomes an empty parameter; `dense_weight()` still
+        returns w_sim, unpacked on demand)."""
+        if self._latent_dropped:
+            return self._packed
+        if not self.weight.is_cuda:
+            raise RuntimeError(f"{type(self).__name__}: move the module to a CUDA device before packing "
+                               "(pb-llm_b200 has no CPU fallback)")
+        w_sim, low_mask, gs = self._effective_weight()
+        self._packed = PackedLinear.from_dense(w_sim, self.bias, low_mask=low_mask, groupsize=gs, verify=verify)
+        self._packed_key = self._key()
+        if not keep_latent:
+            self.weight = nn.Parameter(torch.empty(0, dtype=self.weight.dtype, device=self.weight.device),
+                                       requires_grad=False)
+            self._latent_dropped = True
+        return self._packed
+
+    def packed(self) -> PackedLinear:
+        if self._latent_dropped:
+            return self._packed
+        if self._packed is None or self._packed_key != self._key():
+            self.pack()
+        return self._packed
+
+    def dense_weight(self) -> torch.Tensor:
+        """w_sim as a dense tensor, reconstructed bit-exactly from the packed form."""
+        return self.packed().unpack()
+
+    def forward(self, x):
+        return self.packed().forward(x)
+
+    def to_regular_linear(self):
+        """Bake w_sim into a plain nn.Linear (reference outlier_quantizer.py:108-114)."""
+        w = self.dense_weight()
+        linear = nn.Linear(w.shape[1], w.shape[0], bias=self.bias is not None, device=w.device, dtype=w.dtype)
+        linear.weight.data = w
+        if self.bias is not None:
+            linear.bias.data = self.bias.data.to(w.dtype)
+        return linear
+
+    def extra_repr(self):
+        return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}"
+
+
+class BinaryLinear(_PackedBase):
+    """Reference quantizer.py:75-86: y = F.linear(x, sign(W), b); W cast to fp32 by the ctor."""
+
+    def __init__(self, weight, bias) -> None:
+        super().__init__()
+        self._init_params(weight, bias, cast_fp32=True)
+
+    def _effective_weight(self):
+        return self.weight.data.sign(), None, -1  # STEBinary.forward, quantizer.py:18-21
+
+
+class FdaBinaryLinear(BinaryLinear):
+    """Reference quantizer.py:112-128: forward value identical to BinaryLinear (FdaBinary.forward
+    is torch.sign, :47-51); only the backward differs, which is out of scope."""
+
+
+class XnorBinaryLinear(_PackedBase):
+    """Reference quantizer.py:172-193: w = W - mean_row(W); alpha = mean_row|w|;
+    y = F.linear(x, sign(w) * alpha, b) -- the row mean is NOT added back."""
+
+    def __init__(self, weight, bias) -> None:
+        super().__init__()
+        self._init_params(weight, bias, cast_fp32=True)
+
+    def quant_weight(self, outlier_mask=None):
+        w = self.weight.data
+        w = w - w.mean(-1).view(-1, 1)                       # :183
+        if outlier_mask is not None:
+            w = w * (~outlier_mask)                          # :184-185
+        scaling_factor = w.abs().mean(-1).view(-1, 1)        # :186
+        return w.sign() * scaling_factor                     # :187-188
+
+    def _effective_weight(self):
+        return self.quant_weight(), None, -1
+
+
+class IrBinaryLinear(XnorBinaryLinear):
+    """Reference quantizer.py:89-109: forward value identical to XnorBinaryLinear (IrNetBinary
+    forward is torch.sign, :31-38)."""
+
+
+class PackedFakeQuantLinear(_PackedBase):
+    """A plain nn.Linear holding GPTQ-PB fake-quant weights (what gptq_pb/gptq.py:180-184 writes
+    and the reference then evaluates as a dense fp16 GEMM), served from the packed form.
+    `low_mask` is the mask file gptq.py:108-114 saves (True = binarized); dtype is kept."""
+
+    def __init__(self, weight, bias, low_mask=None, groupsize: int = -1) -> None:
+        super().__init__()
+        self._init_params(weight, bias, cast_fp32=False)
+        self.low_mask = low_mask
+        self.groupsize = groupsize
+
+    @classmethod
+    def from_linear(cls, linear: nn.Linear, low_mask=None, groupsize: int = -1):
+        return cls(linear.weight, linear.bias, low_mask, groupsize)
+
+    def _effective_weight(self):
+        return self.weight.data, self.low_mask, self.groupsize
+
+    @torch.no_grad()
+    def pack(self, keep_latent: bool = True, verify: bool = False):
+        p = super().pack(keep_latent, verify)
+        if not keep_latent:
+            self.low_mask = None
+        return p
