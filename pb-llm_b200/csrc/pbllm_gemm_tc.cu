@@ -1,9 +1,510 @@
-// tcgen05 bit-plane GEMM (prefill regime) -- placeholder until the kernel lands.
+// tcgen05 bit-plane GEMM (prefill regime): y[M,N] = x[M,K] . w_sim[N,K]^T + bias, fp16/bf16.
+//
+// The weight operand never exists densely in HBM: per 64-column k-block each CTA streams the
+// packed planes (0.25 B/weight) + salient values, and 8 "expansion" warps rebuild the EXACT
+// fp16/bf16 w_sim tile (bit -> {lo,hi} select per row, salient values patched in) directly in
+// shared memory in the 128B-swizzled K-major layout tcgen05.mma consumes.  Because the tile is
+// bit-identical to the reference's materialised w_sim, the result differs from the reference's
+// cuBLAS F.linear (quant/quantizer.py:193, quant/outlier_quantizer.py:105) only by fp32
+// summation order.  Activations come in by TMA (SWIZZLE_128B), accumulators live in TMEM.
+//
+// CTA tile: 256 tokens (two UMMA M=128 halves) x 256 weight rows (N=256) x 64 (K block);
+// all 512 TMEM columns hold the two fp32 accumulator halves.  Persistent grid, one CTA per SM.
+// Warp roles: 0 = TMA producer (x), 1 = MMA issuer + TMEM owner, 2..9 = weight expansion
+// (thread = weight row), 10..13 = epilogue (TMEM -> regs -> +bias -> fp16 -> global).
+#include <cuda.h>
+
 #include "pbllm_common.cuh"
+
 namespace pbl {
-bool gemm_tc_supported(const Layer&, const void*, int64_t, const void*, int64_t, int64_t) { return false; }
-int launch_gemm_tc(const Layer&, const void*, int64_t, void*, int64_t, int64_t, cudaStream_t) {
-    set_error("tcgen05 GEMM path not built");
-    return PBL_ERR_UNSUPPORTED;
+
+namespace tc {
+constexpr int BM = 256, BN = 256, BK = 64;
+constexpr int kStages = 3;
+constexpr int kAStage = BM * BK * 2;  // 32 KB
+constexpr int kBStage = BN * BK * 2;  // 32 KB
+constexpr int kExpWarps = 8, kEpiWarps = 4;
+constexpr int kExpThreads = kExpWarps * 32;
+constexpr int kThreads = (2 + kExpWarps + kEpiWarps) * 32;  // 448
+constexpr int kScratchVals = 512;                            // prefetched salient values per (row-group, k-block)
+constexpr int kScratchBytes = kScratchVals * 2;              // two 512 B rows of 16 B lane slots
+constexpr int kOffA = 0;
+constexpr int kOffB = kOffA + kStages * kAStage;
+constexpr int kOffScratch = kOffB + kStages * kBStage;
+constexpr int kOffBar = kOffScratch + kExpWarps * kScratchBytes;
+constexpr int kNumBars = 3 * kStages + 2;
+constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
+constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;  // + slack for 1024 B alignment of the base
+static_assert(kOffBar % 8 == 0, "barrier alignment");
+static_assert(kSmemBytes <= 232448, "exceeds 227 KB");
+}  // namespace tc
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ uint32_t sel_xor_and(uint32_t a, uint32_t b, uint32_t c) {  // a ^ (b & c)
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x78;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint16_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ uint16_t lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 64 16-bit elements = 128 B,
+// 8-row groups 1024 B apart): start>>4 | LBO(1)<<16 | SBO(1024>>4)<<32 | version(1)<<46 | layout(2)<<61
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    const uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+template <typename T> __device__ __forceinline__ uint32_t bits16(float v);
+template <> __device__ __forceinline__ uint32_t bits16<__half>(float v) { return __half_as_ushort(__float2half_rn(v)); }
+template <> __device__ __forceinline__ uint32_t bits16<__nv_bfloat16>(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct GemmParams {
+    const uint4* planes;
+    const uint32_t* vptr;
+    const uint16_t* vals;
+    const float2* affine;
+    const float* bias;
+    void* y;
+    int64_t ldy;
+    int M, N, K;
+    int tiles_r, tiles_c, groups, tiles_per_group;
+    int m_tiles, n_tiles, kblocks;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(tc::kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
+    using namespace tc;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024 B alignment
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = smem_base + kOffBar;
+    auto full_a = [&](int s) { return bar0 + 8u * s; };
+    auto full_b = [&](int s) { return bar0 + 8u * (kStages + s); };
+    auto empty = [&](int s) { return bar0 + 8u * (2 * kStages + s); };
+    const uint32_t tmem_full = bar0 + 8u * (3 * kStages), tmem_empty = bar0 + 8u * (3 * kStages + 1);
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + kOffTmemPtr);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_a(s), 1);
+            mbar_init(full_b(s), kExpThreads);
+            mbar_init(empty(s), 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, kEpiWarps * 32);
+        fence_barrier_init();
+    }
+    if (warp == 1) {  // TMEM: all 512 columns (two 128x256 fp32 accumulator halves)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + kOffTmemPtr), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_tiles = p.m_tiles * p.n_tiles;
+    const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int KB = p.kblocks;
+
+    if (warp == 0) {
+        // ===== TMA producer: x tile [256 tokens x 64] per k-block =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+            int s = 0;
+            uint32_t ph = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int t = blockIdx.x + ti * gridDim.x;
+                const int m0 = (t / p.n_tiles) * BM;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(empty(s), ph ^ 1u);
+                    mbar_arrive_expect_tx(full_a(s), kAStage);
+                    tma_load_2d(smem_base + kOffA + s * kAStage, &tmap_x, kb * BK, m0, full_a(s));
+                    if (++s == kStages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        // instruction descriptor: D=f32, A/B = f16|bf16, both K-major, N=256, M=128
+        const uint32_t fmt = (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value) ? 1u : 0u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+        int s = 0;
+        uint32_t ph = 0, acc_ph = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int t = blockIdx.x + ti * gridDim.x;
+            const int m0 = (t / p.n_tiles) * BM;
+            const int halves = (m0 + 128 < p.M) ? 2 : 1;
+            mbar_wait(tmem_empty, acc_ph ^ 1u);
+            tc_fence_after();
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(full_a(s), ph);
+                mbar_wait(full_b(s), ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_base + kOffA + s * kAStage, b_addr = smem_base + kOffB + s * kBStage;
+                    for (int h = 0; h < halves; ++h) {
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t da = make_sw128_desc(a_addr + h * (128 * 128) + k * 32);
+                            const uint64_t db = make_sw128_desc(b_addr + k * 32);
+                            umma_f16(tmem_base + h * 256, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(empty(s));
+                    if (kb == KB - 1) umma_commit(tmem_full);
+                }
+                __syncwarp();
+                if (++s == kStages) { s = 0; ph ^= 1u; }
+            }
+            acc_ph ^= 1u;
+        }
+    } else if (warp < 2 + kExpWarps) {
+        // ===== weight expansion: thread = weight row of the 256-row tile =====
+        const int e = threadIdx.x - 64;
+        const int ew = e >> 5;                 // expansion warp 0..7 (== row group within the CTA tile)
+        const int r = e & 127;                 // row within its 128-row plane tile
+        const int rgi = r >> 5;                // row group within the plane tile (warp-uniform)
+        const uint32_t r7 = (uint32_t)(e & 7);
+        const uint32_t row_off = (uint32_t)(e >> 3) * 1024u + r7 * 128u;
+        const uint32_t scratch = smem_base + kOffScratch + ew * kScratchBytes;
+        const int64_t total = (int64_t)my_tiles * KB;
+
+        // software pipeline state (explicit rotation, no dynamic register indexing):
+        //   item w: plane word / value range loaded 2 iterations ago, value bytes 1 iteration ago
+        struct Meta { uint4 pw; uint32_t cs, ce; };
+        auto item_tile = [&](int64_t w, int& tr, int& kb, bool& valid) {
+            const int ti = (int)(w / KB);
+            kb = (int)(w - (int64_t)ti * KB);
+            const int t = blockIdx.x + ti * gridDim.x;
+            tr = (t % p.n_tiles) * 2 + (e >> 7);
+            valid = tr < p.tiles_r;
+        };
+        auto load_meta = [&](int64_t w) {   // plane word + value range of item w
+            Meta m;
+            m.pw = make_uint4(0, 0, 0, 0);
+            m.cs = m.ce = 0;
+            if (w < total) {
+                int tr, kb; bool valid;
+                item_tile(w, tr, kb, valid);
+                if (valid) {
+                    const int64_t tile = (int64_t)tr * p.tiles_c + kb;
+                    m.pw = __ldg(p.planes + tile * kTileRows + r);
+                    m.cs = __ldg(p.vptr + tile * kRgPerTile + rgi);
+                    m.ce = __ldg(p.vptr + tile * kRgPerTile + rgi + 1);
+                }
+            }
+            return m;
+        };
+        auto load_vals = [&](const Meta& m, uint4& q0, uint4& q1) {   // coalesced prefetch of the value chunk
+            const uint32_t b0 = (m.cs * 2u) & ~15u, b1 = m.ce * 2u;
+            const uint8_t* base = reinterpret_cast<const uint8_t*>(p.vals);
+            const uint32_t o0 = b0 + 16u * lane, o1 = o0 + 512u;
+            if (o0 < b1) q0 = __ldg(reinterpret_cast<const uint4*>(base + o0));
+            if (o1 < b1) q1 = __ldg(reinterpret_cast<const uint4*>(base + o1));
+        };
+
+        Meta m0 = load_meta(0), m1 = load_meta(1);
+        uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
+        if (total > 0) load_vals(m0, q0, q1);
+
+        int s = 0;
+        uint32_t ph = 0;
+        int cur_g = -1, cur_tr = -1;
+        uint32_t LL = 0, DD = 0;
+        for (int64_t w = 0; w < total; ++w) {
+            int tr, kb; bool valid;
+            item_tile(w, tr, kb, valid);
+            const uint4 pw = m0.pw;
+            const uint32_t cs = m0.cs, ce = m0.ce;
+            const uint4 v0 = q0, v1 = q1;
+            // issue the next items' global loads before touching shared memory
+            const Meta m2 = load_meta(w + 2);
+            if (w + 1 < total) load_vals(m1, q0, q1);
+            m0 = m1;
+            m1 = m2;
+
+            const int g = kb / p.tiles_per_group;
+            if (g != cur_g || tr != cur_tr) {
+                cur_g = g; cur_tr = tr;
+                float2 a = make_float2(0.f, 0.f);
+                if (valid) a = __ldg(p.affine + ((int64_t)tr * kTileRows + r) * p.groups + g);
+                const uint32_t lo = bits16<T>(a.x), hi = bits16<T>(a.y);
+                LL = lo | (lo << 16);
+                DD = (lo ^ hi) * 0x10001u;
+            }
+
+            mbar_wait(empty(s), ph ^ 1u);
+
+            // stage the row group's salient values in the warp scratch
+            __syncwarp();
+            const uint32_t b0 = (cs * 2u) & ~15u;
+            {
+                const uint32_t o0 = 16u * lane, o1 = o0 + 512u;
+                if (b0 + o0 < ce * 2u) sts_v4(scratch + o0, v0.x, v0.y, v0.z, v0.w);
+                if (b0 + o1 < ce * 2u) sts_v4(scratch + o1, v1.x, v1.y, v1.z, v1.w);
+            }
+            __syncwarp();
+
+            // dense part: 64 bits -> 64 exact {lo,hi} values, 8 swizzled 16 B chunks
+            const uint32_t brow = smem_base + kOffB + s * kBStage + row_off;
+#pragma unroll
+            for (int wd = 0; wd < 2; ++wd) {
+                const uint32_t sg = wd ? pw.y : pw.x;
+                const uint32_t X0 = sg, X1 = sg << 1, X2 = sg << 2, X3 = sg << 3, X4 = sg << 4, X5 = sg << 5, X6 = sg << 6,
+                               X7 = sg << 7;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t sel = 0x8888u | (uint32_t)c | ((uint32_t)c << 4) | ((uint32_t)(4 + c) << 8) | ((uint32_t)(4 + c) << 12);
+                    const uint32_t h0 = sel_xor_and(LL, DD, prmt(X7, X6, sel));
+                    const uint32_t h1 = sel_xor_and(LL, DD, prmt(X5, X4, sel));
+                    const uint32_t h2 = sel_xor_and(LL, DD, prmt(X3, X2, sel));
+                    const uint32_t h3 = sel_xor_and(LL, DD, prmt(X1, X0, sel));
+                    sts_v4(brow + ((((uint32_t)(wd * 4 + c)) ^ r7) << 4), h0, h1, h2, h3);
+                }
+            }
+            // salient part: patch the exact stored values over their positions
+            uint32_t idx = (cs - (b0 >> 1)) + warp_excl_scan(__popc(pw.z) + __popc(pw.w), lane);
+#pragma unroll
+            for (int wd = 0; wd < 2; ++wd) {
+                uint32_t mk = wd ? pw.w : pw.z;
+                while (mk) {
+                    const uint32_t j = (uint32_t)__ffs(mk) - 1u;
+                    mk &= mk - 1u;
+                    uint16_t v;
+                    if (idx < (uint32_t)kScratchVals) v = lds_u16(scratch + idx * 2u);
+                    else v = __ldg(p.vals + (b0 >> 1) + idx);
+                    ++idx;
+                    const uint32_t col = (uint32_t)wd * 32u + j;
+                    sts_u16(brow + ((col << 1) ^ (r7 << 4)), v);
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(full_b(s));
+            if (++s == kStages) { s = 0; ph ^= 1u; }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> (+bias) -> 16-bit -> global =====
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        uint32_t acc_ph = 0;
+        T* y = reinterpret_cast<T*>(p.y);
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int t = blockIdx.x + ti * gridDim.x;
+            const int m0 = (t / p.n_tiles) * BM, n0 = (t % p.n_tiles) * BN;
+            const int halves = (m0 + 128 < p.M) ? 2 : 1;
+            mbar_wait(tmem_full, acc_ph);
+            tc_fence_after();
+            for (int h = 0; h < halves; ++h) {
+                const int m = m0 + h * 128 + q * 32 + lane;
+#pragma unroll 1
+                for (int cb = 0; cb < BN / 32; ++cb) {
+                    const int n = n0 + cb * 32;
+                    if (n >= p.N) break;  // warp-uniform
+                    uint32_t acc[32];
+                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256 + cb * 32), acc);
+                    tmem_ld_wait();
+                    if (m < p.M) {
+                        T* yrow = y + (int64_t)m * p.ldy + n;
+#pragma unroll
+                        for (int v8 = 0; v8 < 4; ++v8) {
+                            if (n + v8 * 8 + 8 <= p.N) {
+                                float f[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(acc[v8 * 8 + i]);
+                                if (p.bias) {
+                                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n + v8 * 8));
+                                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + v8 * 8 + 4));
+                                    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                                    f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                                }
+                                uint4 o;
+                                o.x = pack2<T>(f[0], f[1]); o.y = pack2<T>(f[2], f[3]);
+                                o.z = pack2<T>(f[4], f[5]); o.w = pack2<T>(f[6], f[7]);
+                                *reinterpret_cast<uint4*>(yrow + v8 * 8) = o;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tmem_empty);
+            acc_ph ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+bool gemm_tc_supported(const Layer& L, const void* x, int64_t ldx, const void* y, int64_t ldy, int64_t M) {
+    if (L.dtype != PBL_F16 && L.dtype != PBL_BF16) return false;
+    if (M <= 0 || M > (1 << 30)) return false;
+    if (L.N % 8 != 0 || ldy % 8 != 0 || ldx % 8 != 0) return false;
+    if (x && (reinterpret_cast<uintptr_t>(x) & 15u)) return false;
+    if (y && (reinterpret_cast<uintptr_t>(y) & 15u)) return false;
+    if (L.bias && (reinterpret_cast<uintptr_t>(L.bias) & 15u)) return false;
+    if (L.groups > 1 && L.groupsize % tc::BK != 0) return false;
+    return true;
+}
+
+int launch_gemm_tc(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled driver entry point unavailable"); return PBL_ERR_CUDA; }
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)L.K, (cuuint64_t)M};
+    const cuuint64_t gstr[1] = {(cuuint64_t)ldx * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BM};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = enc(&tmap, L.dtype == PBL_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                      const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return PBL_ERR_CUDA; }
+
+    GemmParams p;
+    p.planes = L.planes; p.vptr = L.vptr; p.vals = reinterpret_cast<const uint16_t*>(L.vals); p.affine = L.affine;
+    p.bias = L.bias; p.y = y; p.ldy = ldy; p.M = (int)M; p.N = (int)L.N; p.K = (int)L.K;
+    p.tiles_r = (int)L.tiles_r; p.tiles_c = (int)L.tiles_c; p.groups = (int)L.groups; p.tiles_per_group = L.tiles_per_group;
+    p.m_tiles = (int)((M + tc::BM - 1) / tc::BM);
+    p.n_tiles = (int)((L.N + tc::BN - 1) / tc::BN);
+    p.kblocks = (int)L.tiles_c;
+
+    static int num_sms = 0;
+    static bool attr_set[2] = {false, false};
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int which = L.dtype == PBL_F16 ? 0 : 1;
+    auto kern = which == 0 ? gemm_tc_kernel<__half> : gemm_tc_kernel<__nv_bfloat16>;
+    if (!attr_set[which]) {
+        int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes),
+                            "cudaFuncSetAttribute(smem)");
+        if (rc) return rc;
+        attr_set[which] = true;
+    }
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    kern<<<grid, tc::kThreads, tc::kSmemBytes, s>>>(tmap, p);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "gemm_tc launch");
+}
+
 }  // namespace pbl

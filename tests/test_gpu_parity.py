@@ -1,0 +1,327 @@
+"""Parity tests proper (need a B200): the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs, against the golden fixtures made from the executed reference,
+and -- at BASELINE.json's full layer sizes -- through size-independent properties.
+
+Tolerance (BASELINE.json north_star): 1e-3 relative, fp16. Written here as
+    max|y - y_ref| / max|y_ref| <= 1e-3      (max-normalised; SURVEY.md 7 "Tolerance definition")
+for fp16/bf16 I/O (bf16 outputs round at 2^-9, so its bound is 4e-3), and 2e-5 for fp32 I/O.
+Packing is integer/bit work: unpack(pack(w)) must be bit-exact."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pbllm_b200 as pb
+from pbllm_b200 import _lib
+from oracle import oracle as orc
+from oracle.gen_golden import make_weight, make_x
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+TOL = {torch.float16: 1e-3, torch.bfloat16: 4e-3, torch.float32: 2e-5}
+
+
+def load(name):
+    return np.load(os.path.join(G, name + ".npz"), allow_pickle=False)
+
+
+def t(a, dtype=None):
+    x = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return x if dtype is None else x.to(dtype)
+
+
+def relmax(y, ref):
+    y = y.detach().float().cpu().numpy().astype(np.float64)
+    ref = np.asarray(ref, np.float64)
+    return float(np.abs(y - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def rms_rel(y, ref):
+    y = y.detach().float().cpu().numpy().astype(np.float64)
+    ref = np.asarray(ref, np.float64)
+    return float(np.sqrt(((y - ref) ** 2).mean()) / max(np.sqrt((ref ** 2).mean()), 1e-30))
+
+
+def rounded(a, dtype):
+    """numpy fp32 array holding dtype-representable values (what the device tensor really holds)."""
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dtype).float().numpy()
+
+
+def test_native_library_is_the_one_running():
+    lib = _lib.load()
+    assert lib.pbl_device_check() == 0, _lib.last_error()
+    n0 = lib.pbl_launch_count()
+    p = pb.PackedLinear.from_dense(torch.randn(64, 64, device=DEV, dtype=torch.float16).sign())
+    p.forward(torch.randn(1, 64, device=DEV, dtype=torch.float16))
+    torch.cuda.synchronize()
+    assert lib.pbl_launch_count() >= n0 + 5   # affine, planes, scan, vals, forward
+
+
+# ---- packing: bit-exact ------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("N,K,gs", [(128, 64, -1), (96, 160, -1), (100, 70, -1), (1, 1, -1), (300, 520, -1),
+                                    (256, 512, 128), (130, 384, 64), (4096, 4096, -1)])
+def test_pack_unpack_roundtrip_bit_exact(dtype, N, K, gs):
+    gen = torch.Generator(device="cpu").manual_seed(N * 131 + K)
+    groups = 1 if gs <= 0 else (K + gs - 1) // gs
+    gse = K if gs <= 0 else gs
+    mu = torch.randn(N, groups, generator=gen) * 0.01
+    al = torch.rand(N, groups, generator=gen) * 0.02 + 0.005
+    sign = (torch.rand(N, K, generator=gen) < 0.5).float() * 2 - 1
+    gi = torch.arange(K) // gse
+    w = (mu[:, gi] + al[:, gi] * sign).to(dtype)
+    low = torch.rand(N, K, generator=gen) < 0.9
+    sal_vals = (torch.randn(N, K, generator=gen) * 0.05).to(dtype)
+    w = torch.where(low, w, sal_vals)
+    w[torch.rand(N, K, generator=gen) < 0.002] = 0               # third values (sign(0) zeros)
+    wd = w.to(DEV)
+    p = pb.PackedLinear.from_dense(wd, None, low_mask=low.to(DEV), groupsize=gs)
+    assert torch.equal(p.unpack(), wd)
+    frac = p.nnz / (N * K)
+    assert 0.05 < frac < 0.2 or N * K < 4096
+    p2 = pb.PackedLinear.from_dense(wd, None, low_mask=None, groupsize=gs)   # mask-free: min/max levels only
+    assert torch.equal(p2.unpack(), wd)
+
+
+def test_pack_levels_and_counts_against_numpy():
+    rs = np.random.RandomState(5)
+    N, K = 200, 330
+    w = np.where(rs.rand(N, K) < 0.5, 0.25, -0.5).astype(np.float32)
+    sal = rs.rand(N, K) < 0.1
+    w[sal] = rs.standard_normal(sal.sum()).astype(np.float32)
+    p = pb.PackedLinear.from_dense(t(w), None, low_mask=t(~sal))
+    assert p.nnz == int(sal.sum())
+    aff = p.affine.view(-1, 2).cpu().numpy()
+    assert np.array_equal(aff[:N, 0], np.full(N, -0.5, np.float32)) and np.array_equal(aff[:N, 1], np.full(N, 0.25, np.float32))
+    assert np.array_equal(aff[N:], np.zeros_like(aff[N:]))
+    planes = p.planes.view(-1, 4).cpu().numpy().view(np.uint32)
+    # tile (0,0), row 3: sign / salient bits of columns 0..63
+    row = planes[3]
+    bits = np.array([(row[j // 32] >> (j % 32)) & 1 for j in range(64)])
+    salb = np.array([(row[2 + j // 32] >> (j % 32)) & 1 for j in range(64)])
+    assert np.array_equal(salb, sal[3, :64].astype(int))
+    assert np.array_equal(bits, ((w[3, :64] == 0.25) & ~sal[3, :64]).astype(int))
+    vptr = p.vptr.cpu().numpy().view(np.uint32)
+    assert vptr[0] == 0 and vptr[-1] == p.nnz and np.all(np.diff(vptr.astype(np.int64)) >= 0)
+    v0 = p.vals[: int(vptr[1])].cpu().numpy()
+    exp = np.concatenate([w[r, :64][sal[r, :64]] for r in range(32)])
+    assert np.array_equal(v0, exp)                                 # (tile, row-group, row, column) order
+
+
+# ---- forward vs oracle ---------------------------------------------------------------------------
+def synth_wsim(N, K, gs, dtype, seed, sal_frac=0.1):
+    rs = np.random.RandomState(seed)
+    groups = 1 if gs <= 0 else (K + gs - 1) // gs
+    gse = K if gs <= 0 else gs
+    gi = np.arange(K) // gse
+    mu = rs.standard_normal((N, groups)) * 0.004
+    al = rs.rand(N, groups) * 0.02 + 0.005
+    w = mu[:, gi] + al[:, gi] * np.where(rs.rand(N, K) < 0.5, 1.0, -1.0)
+    low = rs.rand(N, K) >= sal_frac
+    w = np.where(low, w, rs.standard_t(3, (N, K)) * 0.03)
+    w = rounded(w.astype(np.float32), dtype)
+    return w, low
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("N,K,gs,M", [(128, 64, -1, 1), (96, 160, -1, 3), (100, 70, -1, 5), (300, 520, -1, 8),
+                                      (256, 512, 128, 2), (768, 768, -1, 1), (768, 768, -1, 4), (768, 3072, -1, 16),
+                                      (33, 2048, -1, 1), (512, 1024, 256, 37)])
+def test_forward_matches_oracle(dtype, N, K, gs, M):
+    w, low = synth_wsim(N, K, gs, dtype, seed=N + K + M)
+    b = rounded(np.random.RandomState(1).standard_normal(N).astype(np.float32) * 0.1, dtype)
+    x = rounded(make_x(N * 7 + M, (M, K)), dtype)
+    ref = orc.linear(x, w, b)
+    for mask in (low, None):
+        p = pb.PackedLinear.from_dense(t(w, dtype), t(b, dtype), None if mask is None else t(mask), gs)
+        y = p.forward(t(x, dtype))
+        assert y.shape == (M, N) and y.dtype == dtype
+        assert relmax(y, ref) <= TOL[dtype], (relmax(y, ref), rms_rel(y, ref))
+        assert rms_rel(y, ref) <= TOL[dtype]
+
+
+def test_forward_shapes_strides_and_errors():
+    w, low = synth_wsim(96, 160, -1, torch.float16, 3)
+    p = pb.PackedLinear.from_dense(t(w, torch.float16), None, t(low))
+    x = t(make_x(9, (2, 3, 160)), torch.float16)
+    y = p.forward(x)
+    assert y.shape == (2, 3, 96)
+    ref = orc.linear(rounded(make_x(9, (2, 3, 160)), torch.float16), w)
+    assert relmax(y, ref) <= 1e-3
+    big = t(make_x(10, (6, 320)), torch.float16)
+    xs = big[:, :160]                                             # row stride 320 (ldx > K)
+    assert relmax(p.forward(xs), orc.linear(xs.float().cpu().numpy(), w)) <= 1e-3
+    xt = t(make_x(11, (160, 6)), torch.float16).t()              # non-unit inner stride -> made contiguous
+    assert relmax(p.forward(xt), orc.linear(xt.float().cpu().numpy(), w)) <= 1e-3
+    assert p.forward(torch.empty(0, 160, device=DEV, dtype=torch.float16)).shape == (0, 96)   # empty input
+    with pytest.raises(RuntimeError, match="dtype"):
+        p.forward(x.float())                                       # mixed dtypes raise, as in the reference
+    with pytest.raises(RuntimeError, match="in_features"):
+        p.forward(x[..., :100])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        p.forward(x.cpu())
+    lib = _lib.load()
+    assert lib.pbl_linear_forward(p.handle, None, 160, None, 96, 4, None) == -1
+    assert lib.pbl_linear_forward(p.handle, C.c_void_p(x.data_ptr()), 100, C.c_void_p(y.data_ptr()), 96, 4, None) == -3
+
+
+# ---- golden fixtures from the executed reference --------------------------------------------------
+def test_golden_cfg1_xnor_768_drop_in_ctor():
+    """BASELINE config 1: OPT-125m-shaped 768x768 XnorBinaryLinear, fp32 as constructed."""
+    g = load("cfg1_xnor_768")
+    seed = int(g["seed"])
+    W, b, x = make_weight(seed, 768, 768), make_x(seed + 1, (768,)) * 0.1, make_x(seed + 2, (4, 768))
+    m = pb.XnorBinaryLinear(torch.from_numpy(W), torch.from_numpy(b)).to(DEV)
+    y = m(t(x))
+    assert relmax(y, g["y"]) <= 2e-5
+    ws = m.dense_weight()
+    bits = np.packbits((ws > 0).cpu().numpy(), axis=-1, bitorder="little")
+    assert np.array_equal(bits, g["sign_bits"])                    # the reference's own sign bits
+    yb = pb.BinaryLinear(torch.from_numpy(W), torch.from_numpy(b)).to(DEV)(t(x))
+    assert relmax(yb, g["y_binary"]) <= 2e-5
+    for M in (1, 4, 2048):                                          # SURVEY 7 minimum slice, fp32 and fp16
+        xm = make_x(77 + M, (M, 768))
+        ref = orc.forward_xnor(xm, W, b)
+        assert relmax(m(t(xm)), ref) <= 2e-5
+    mh = pb.XnorBinaryLinear(torch.from_numpy(W), torch.from_numpy(b)).to(DEV)
+    ph = pb.PackedLinear.from_dense(mh.quant_weight().half(), mh.bias.data)
+    xm = rounded(make_x(5, (4, 768)), torch.float16)
+    ref = orc.linear(xm, mh.quant_weight().half().float().cpu().numpy(), b)
+    assert relmax(ph.forward(t(xm, torch.float16)), ref) <= 1e-3
+
+
+def test_golden_quantizer_small_all_classes():
+    g = load("quantizer_small")
+    W, b, x = torch.from_numpy(g["W"]), torch.from_numpy(g["b"]), t(g["x"])
+    for name in ["BinaryLinear", "XnorBinaryLinear", "IrBinaryLinear", "FdaBinaryLinear"]:
+        m = getattr(pb, name)(W, b).to(DEV)
+        y = m(x)
+        assert y.shape == (2, 3, 96)
+        assert relmax(y, g["y_" + name]) <= 2e-5, name
+    assert relmax(pb.XnorBinaryLinear(W, None).to(DEV)(x), g["y_Xnor_nobias"]) <= 2e-5
+    m = pb.XnorBinaryLinear(W, b).to(DEV)
+    assert torch.equal(m.dense_weight().cpu(), torch.from_numpy(g["wsim_Xnor"])) or \
+        relmax(m.dense_weight(), g["wsim_Xnor"]) < 5e-7            # GPU reduction order may move alpha by an ulp
+    lin = m.to_regular_linear()
+    assert relmax(lin(x), g["y_XnorBinaryLinear"]) <= 2e-5
+
+
+@pytest.mark.parametrize("tag", ["outlier_f32_small", "outlier_f16_small", "outlier_f32_heavy", "outlier_f16_heavy"])
+def test_golden_outlier_drop_in_ctor(tag):
+    g = load(tag)
+    half = g["W"].dtype == np.float16
+    dtype = torch.float16 if half else torch.float32
+    m = pb.BinaryXnorExceptOutliersLinear(torch.from_numpy(g["W"]).clone(), torch.from_numpy(g["b"]), float(g["frac"]))
+    m = m.to(DEV).eval()
+    y = m(t(g["x"]))
+    assert torch.equal(m.outlier_mask.cpu(), torch.from_numpy(g["mask"]))
+    if half:   # 8-bit codes incl. the uint8 wrap: bit-exact once rounded to fp16
+        assert torch.equal(m.weight.data.float().cpu(), torch.from_numpy(g["w8"]))
+    else:      # fp32 dequant q*(range/255)+zp is FMA-contracted by torch's CUDA kernel: <= 1 ulp off the CPU fixture
+        assert relmax(m.weight.data, g["w8"]) <= 2e-7
+    ws = m.dense_weight().float().cpu().numpy()
+    assert relmax(torch.from_numpy(ws[g["mask"]]), g["wsim"][g["mask"]]) <= (0 if half else 2e-7)
+    assert relmax(torch.from_numpy(ws), g["wsim"]) <= (1e-3 if half else 5e-7)   # alpha: reduction order
+    assert relmax(y, g["y"]) <= (3e-3 if half else 2e-5)            # golden y is the reference's CPU fp16 GEMM
+    ref = orc.linear(g["x"].astype(np.float32), ws, g["b"].astype(np.float32))
+    assert relmax(y, ref) <= TOL[dtype]
+    assert abs(m.outlier_nbits - float(g["nbits"])) < 1e-12
+    p = m.packed()
+    assert p.nnz >= int(g["mask"].sum())
+    reg = m.to_regular_linear()
+    assert torch.equal(reg.weight.data, m.dense_weight())
+    m.pack(keep_latent=False)
+    assert m.weight.numel() == 0 and relmax(m(t(g["x"])), ref) <= TOL[dtype]
+
+
+def test_golden_outlier_768_known_answers():
+    g = load("outlier_768_kat")
+    W = make_weight(int(g["seed"]), 768, 768)
+    m = pb.BinaryXnorExceptOutliersLinear(torch.from_numpy(W).clone(), None, 0.1).to(DEV).eval()
+    y = m(t(make_x(33, (4, 768))))
+    assert int(m.outlier_mask.sum()) == 58982
+    assert np.array_equal(np.packbits(m.outlier_mask.cpu().numpy(), axis=-1, bitorder="little"), g["mask_bits"])
+    assert abs(m.outlier_nbits - 1.6104193793402777) < 1e-12
+    ws = m.dense_weight()
+    assert int((ws < 0).sum()) == 0 and int((ws == 0).sum()) == int(g["n_zero"])
+    assert relmax(y, g["y"]) <= 2e-5
+    p = m.packed()
+    aff = p.affine.view(-1, 2)[:768].cpu().numpy()
+    assert np.all(aff[:, 0] == 0.0) and np.allclose(aff[:, 1], float(g["binary_scale"]), rtol=1e-6)  # levels {0, alpha}
+    assert p.nnz == 58982                                           # zeros are a LEVEL here, not residual
+
+
+def test_golden_hessian_mask(tmp_path, monkeypatch):
+    g = load("hessian_mask")
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("gptq_pb/outputs/mask")
+    torch.save(torch.from_numpy(g["low_mask"]), "gptq_pb/outputs/mask/mask_0.9_synthetic_model.layers.0.q_proj.pkl")
+    m = pb.BinaryXnorExceptOutliersLinearHessian(torch.from_numpy(g["W"]).clone(), None, 0.1).to(DEV)
+    m.global_name = "synthetic/model.layers.0.q_proj"
+    m.eval()
+    m.gen_outlier_mask()
+    with pytest.raises(TypeError):
+        m(t(g["x"]))
+    m.train()
+    assert relmax(m(t(g["x"])), g["y_train"]) <= 2e-5
+    m.eval()
+    assert relmax(m(t(g["x"])), g["y_eval"]) <= 2e-5
+    m2 = pb.BinaryXnorExceptOutliersLinearHessian(torch.from_numpy(g["W"]).clone(), None, 0.1).to(DEV).eval()
+    m2.global_name = "synthetic/missing"
+    assert relmax(m2(t(g["x"])), g["y_fallback"]) <= 2e-5
+
+
+@pytest.mark.parametrize("tag", ["gptqpb_rtn_g-1_mag", "gptqpb_rtn_g128_hes", "gptqpb_gptq_g-1_hes",
+                                 "gptqpb_gptq_g128_mag"])
+def test_golden_gptqpb_fakequant_layers(tag):
+    g = load(tag)
+    gs = int(g["groupsize"])
+    lin = torch.nn.Linear(256, 48, bias=False, device=DEV, dtype=torch.float16)
+    lin.weight.data = t(g["Wq"])
+    m = pb.PackedFakeQuantLinear.from_linear(lin, t(g["low_mask"]), gs)
+    y = m(t(g["x"]))
+    assert relmax(y, g["y"]) <= 1e-3
+    assert torch.equal(m.dense_weight(), lin.weight.data)           # exact weights, only the sum order differs
+    p = m.packed()
+    sal = int((~g["low_mask"]).sum())
+    assert sal <= p.nnz <= sal + 0.01 * g["Wq"].size               # + rare third value mu (sign(0))
+    m2 = pb.PackedFakeQuantLinear.from_linear(lin, None, gs)       # no mask file: levels from min/max
+    assert relmax(m2(t(g["x"])), g["y"]) <= 1e-3
+
+
+# ---- end-to-end host-buffer entry point ---------------------------------------------------------
+def test_forward_host_buffers():
+    w, low = synth_wsim(256, 512, -1, torch.float16, 8)
+    p = pb.PackedLinear.from_dense(t(w, torch.float16), None, t(low))
+    xh = torch.from_numpy(make_x(2, (6, 512))).half().pin_memory()
+    yh = torch.empty(6, 256, dtype=torch.float16).pin_memory()
+    ws = torch.empty(p.host_workspace_bytes(6), dtype=torch.uint8, device=DEV)
+    p.forward_host(xh, yh, ws)
+    assert relmax(yh, orc.linear(xh.float().numpy(), w)) <= 1e-3
+
+
+# ---- BASELINE.json full layer sizes: size-independent properties --------------------------------
+@pytest.mark.parametrize("N,K", [(4096, 4096), (11008, 4096), (4096, 11008)])
+@pytest.mark.parametrize("M", [1, 8])
+def test_full_size_properties_llama7b_shapes(N, K, M):
+    gen = torch.Generator(device=DEV).manual_seed(N + K)
+    al = torch.rand(N, 1, device=DEV, generator=gen) * 0.02 + 0.005
+    mu = torch.randn(N, 1, device=DEV, generator=gen) * 0.003
+    w = (mu + al * (torch.rand(N, K, device=DEV, generator=gen) < 0.5).float().mul(2).sub(1)).half()
+    low = torch.rand(N, K, device=DEV, generator=gen) < 0.9
+    w = torch.where(low, w, (torch.randn(N, K, device=DEV, generator=gen) * 0.03).half())
+    p = pb.PackedLinear.from_dense(w, None, low)
+    assert torch.equal(p.unpack(), w)                               # round trip at full size
+    assert abs(p.nnz / (N * K) - 0.1) < 0.005
+    x1 = torch.randn(M, K, device=DEV, generator=gen).half()
+    x2 = torch.randn(M, K, device=DEV, generator=gen).half()
+    y1, y2 = p.forward(x1).float(), p.forward(x2).float()
+    y12 = p.forward((x1.float() + x2.float()).half()).float()       # linearity (up to fp16 rounding of x1+x2, y)
+    scale = y12.abs().max()
+    assert ((y1 + y2 - y12).abs().max() / scale) < 4e-3
+    ref = x1.double() @ w.double().t()                              # dense fp64 check of the same w_sim
+    assert ((y1.double() - ref).abs().max() / ref.abs().max()) <= 1e-3
+    assert torch.equal(p.forward(x1), p.forward(x1))                # deterministic (no atomics)
