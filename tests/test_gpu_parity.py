@@ -168,6 +168,42 @@ def test_forward_shapes_strides_and_errors():
     assert lib.pbl_linear_forward(p.handle, C.c_void_p(x.data_ptr()), 100, C.c_void_p(y.data_ptr()), 96, 4, None) == -3
 
 
+# ---- tcgen05 GEMM path (M above the skinny-kernel threshold) ---------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N,K,gs,M,bias", [(256, 64, -1, 16, False), (256, 256, -1, 128, True), (256, 256, -1, 129, False),
+                                           (264, 520, -1, 300, True), (768, 768, -1, 1000, True), (512, 1024, 256, 37, False),
+                                           (128, 4096, -1, 256, False), (1024, 11008, -1, 64, False),
+                                           (4096, 4096, -1, 512, False)])
+def test_gemm_tc_matches_oracle(dtype, N, K, gs, M, bias):
+    w, low = synth_wsim(N, K, gs, dtype, seed=N + K + M)
+    b = rounded(np.random.RandomState(2).standard_normal(N).astype(np.float32) * 0.1, dtype) if bias else None
+    x = rounded(make_x(N * 3 + M, (M, K)), dtype)
+    p = pb.PackedLinear.from_dense(t(w, dtype), None if b is None else t(b, dtype), t(low), gs)
+    assert p.select_kernel(M) == 1                                  # tcgen05 path is the one selected
+    y = p.forward(t(x, dtype))
+    if M * N * K <= 4e8:
+        ref = orc.linear(x, w, b)                                   # CPU oracle (double accumulate)
+    else:                                                           # large: fp64 on device over the same w_sim
+        ref = (t(x).double() @ t(w).double().t() + (0 if b is None else t(b).double())).cpu().numpy()
+    assert relmax(y, ref) <= TOL[dtype], (relmax(y, ref), rms_rel(y, ref))
+    assert rms_rel(y, ref) <= TOL[dtype]
+    os.environ["PBL_FORCE_KERNEL"] = "0"                            # both kernels agree on the same packed layer
+    try:
+        y0 = p.forward(t(x, dtype))
+    finally:
+        os.environ.pop("PBL_FORCE_KERNEL")
+    assert relmax(y, y0.float().cpu().numpy()) <= 2 * TOL[dtype]
+
+
+def test_gemm_tc_one_hot_activations_reproduce_w_sim_exactly():
+    """x = I  =>  y = w_sim^T bit-for-bit: the expanded tile IS the reference's tensor."""
+    w, low = synth_wsim(512, 256, -1, torch.float16, 77)
+    p = pb.PackedLinear.from_dense(t(w, torch.float16), None, t(low))
+    y = p.forward(torch.eye(256, device=DEV, dtype=torch.float16))
+    assert p.select_kernel(256) == 1
+    assert torch.equal(y, t(w, torch.float16).t())
+
+
 # ---- golden fixtures from the executed reference --------------------------------------------------
 def test_golden_cfg1_xnor_768_drop_in_ctor():
     """BASELINE config 1: OPT-125m-shaped 768x768 XnorBinaryLinear, fp32 as constructed."""
