@@ -10,8 +10,9 @@
 //
 // CTA tile: 256 tokens (two UMMA M=128 halves) x 256 weight rows (N=256) x 64 (K block);
 // all 512 TMEM columns hold the two fp32 accumulator halves.  Persistent grid, one CTA per SM.
-// Warp roles: 0 = TMA producer (x), 1 = MMA issuer + TMEM owner, 2..9 = weight expansion
-// (thread = weight row), 10..13 = epilogue (TMEM -> regs -> +bias -> fp16 -> global).
+// Warp roles: 0 = TMA producer (x), 1 = MMA issuer + TMEM owner, 2..17 = weight expansion
+// (two teams of 8 warps on alternate k-blocks; thread = weight row), 18..21 = epilogue
+// (TMEM -> regs -> +bias -> fp16 -> global).
 #include <cuda.h>
 
 #include "pbllm_common.cuh"
@@ -23,9 +24,11 @@ constexpr int BM = 256, BN = 256, BK = 64;
 constexpr int kStages = 3;
 constexpr int kAStage = BM * BK * 2;  // 32 KB
 constexpr int kBStage = BN * BK * 2;  // 32 KB
-constexpr int kExpWarps = 8, kEpiWarps = 4;
-constexpr int kExpThreads = kExpWarps * 32;
-constexpr int kThreads = (2 + kExpWarps + kEpiWarps) * 32;  // 448
+constexpr int kTeams = 2;                                     // expansion teams (alternate k-blocks)
+constexpr int kExpWarps = 8 * kTeams, kEpiWarps = 4;
+constexpr int kExpThreads = 256;                              // arrivals per B stage (one team)
+static_assert(kTeams <= kStages, "teams must not outnumber stages");
+constexpr int kThreads = (2 + kExpWarps + kEpiWarps) * 32;  // 704
 constexpr int kScratchVals = 512;                            // prefetched salient values per (row-group, k-block)
 constexpr int kScratchBytes = kScratchVals * 2;              // two 512 B rows of 16 B lane slots
 constexpr int kOffA = 0;
@@ -252,39 +255,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
             acc_ph ^= 1u;
         }
     } else if (warp < 2 + kExpWarps) {
-        // ===== weight expansion: thread = weight row of the 256-row tile =====
-        const int e = threadIdx.x - 64;
-        const int ew = e >> 5;                 // expansion warp 0..7 (== row group within the CTA tile)
+        // ===== weight expansion: thread = weight row of the 256-row tile; kTeams teams of 8 warps
+        //       take alternate k-blocks so two shared-memory stages are being filled concurrently =====
+        const int et = threadIdx.x - 64;
+        const int team = et >> 8;              // 0..kTeams-1
+        const int e = et & 255;                // weight row within the CTA tile
+        const int ew = et >> 5;                // expansion warp (own scratch)
         const int r = e & 127;                 // row within its 128-row plane tile
         const int rgi = r >> 5;                // row group within the plane tile (warp-uniform)
         const uint32_t r7 = (uint32_t)(e & 7);
         const uint32_t row_off = (uint32_t)(e >> 3) * 1024u + r7 * 128u;
         const uint32_t scratch = smem_base + kOffScratch + ew * kScratchBytes;
-        const int64_t total = (int64_t)my_tiles * KB;
+        const bool grouped = p.groups > 1;
 
-        // software pipeline state (explicit rotation, no dynamic register indexing):
-        //   item w: plane word / value range loaded 2 iterations ago, value bytes 1 iteration ago
-        struct Meta { uint4 pw; uint32_t cs, ce; };
-        auto item_tile = [&](int64_t w, int& tr, int& kb, bool& valid) {
-            const int ti = (int)(w / KB);
-            kb = (int)(w - (int64_t)ti * KB);
-            const int t = blockIdx.x + ti * gridDim.x;
-            tr = (t % p.n_tiles) * 2 + (e >> 7);
-            valid = tr < p.tiles_r;
+        // item = (tile index ti, k-block kb); this team handles items team, team+kTeams, ... of the
+        // CTA's flattened (tile, k-block) sequence.  Cursor arithmetic is incremental (no divisions).
+        struct Meta { uint4 pw; uint32_t cs, ce; int tr, g; };
+        int c_ti = 0, c_kb = team;             // prefetch cursor
+        auto cursor_norm = [&]() {
+            while (c_kb >= KB && c_ti < my_tiles) { c_kb -= KB; ++c_ti; }
         };
-        auto load_meta = [&](int64_t w) {   // plane word + value range of item w
+        auto load_meta = [&]() {               // loads the cursor's item and advances the cursor
             Meta m;
             m.pw = make_uint4(0, 0, 0, 0);
             m.cs = m.ce = 0;
-            if (w < total) {
-                int tr, kb; bool valid;
-                item_tile(w, tr, kb, valid);
-                if (valid) {
-                    const int64_t tile = (int64_t)tr * p.tiles_c + kb;
+            m.tr = -1; m.g = 0;
+            cursor_norm();
+            if (c_ti < my_tiles) {
+                const int t = blockIdx.x + c_ti * gridDim.x;
+                const int tr = (t % p.n_tiles) * 2 + (e >> 7);
+                if (tr < p.tiles_r) {
+                    const int64_t tile = (int64_t)tr * p.tiles_c + c_kb;
                     m.pw = __ldg(p.planes + tile * kTileRows + r);
                     m.cs = __ldg(p.vptr + tile * kRgPerTile + rgi);
                     m.ce = __ldg(p.vptr + tile * kRgPerTile + rgi + 1);
+                    m.tr = tr;
+                    m.g = grouped ? c_kb / p.tiles_per_group : 0;
                 }
+                c_kb += kTeams;
             }
             return m;
         };
@@ -296,31 +304,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
             if (o1 < b1) q1 = __ldg(reinterpret_cast<const uint4*>(base + o1));
         };
 
-        Meta m0 = load_meta(0), m1 = load_meta(1);
+        const int64_t total = (int64_t)my_tiles * KB;
+        const int64_t my_items = (total - team + kTeams - 1) / kTeams;
+        Meta m0 = load_meta(), m1 = load_meta();
         uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
-        if (total > 0) load_vals(m0, q0, q1);
+        if (my_items > 0) load_vals(m0, q0, q1);
 
-        int s = 0;
+        int s = team % kStages;
         uint32_t ph = 0;
-        int cur_g = -1, cur_tr = -1;
+        int cur_g = -1, cur_tr = -2;
         uint32_t LL = 0, DD = 0;
-        for (int64_t w = 0; w < total; ++w) {
-            int tr, kb; bool valid;
-            item_tile(w, tr, kb, valid);
+        for (int64_t it = 0; it < my_items; ++it) {
             const uint4 pw = m0.pw;
             const uint32_t cs = m0.cs, ce = m0.ce;
+            const int tr = m0.tr, g = m0.g;
             const uint4 v0 = q0, v1 = q1;
             // issue the next items' global loads before touching shared memory
-            const Meta m2 = load_meta(w + 2);
-            if (w + 1 < total) load_vals(m1, q0, q1);
+            const Meta m2 = load_meta();
+            if (it + 1 < my_items) load_vals(m1, q0, q1);
             m0 = m1;
             m1 = m2;
 
-            const int g = kb / p.tiles_per_group;
             if (g != cur_g || tr != cur_tr) {
                 cur_g = g; cur_tr = tr;
                 float2 a = make_float2(0.f, 0.f);
-                if (valid) a = __ldg(p.affine + ((int64_t)tr * kTileRows + r) * p.groups + g);
+                if (tr >= 0) a = __ldg(p.affine + ((int64_t)tr * kTileRows + r) * p.groups + g);
                 const uint32_t lo = bits16<T>(a.x), hi = bits16<T>(a.y);
                 LL = lo | (lo << 16);
                 DD = (lo ^ hi) * 0x10001u;
@@ -356,24 +364,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
                 }
             }
             // salient part: patch the exact stored values over their positions
-            uint32_t idx = (cs - (b0 >> 1)) + warp_excl_scan(__popc(pw.z) + __popc(pw.w), lane);
+            const uint32_t idx0 = (cs - (b0 >> 1)) + warp_excl_scan(__popc(pw.z) + __popc(pw.w), lane);
+            if (ce - (b0 >> 1) <= (uint32_t)kScratchVals) {   // warp-uniform: whole chunk is staged in scratch
+                uint32_t sa = scratch + idx0 * 2u;
 #pragma unroll
-            for (int wd = 0; wd < 2; ++wd) {
-                uint32_t mk = wd ? pw.w : pw.z;
-                while (mk) {
-                    const uint32_t j = (uint32_t)__ffs(mk) - 1u;
-                    mk &= mk - 1u;
-                    uint16_t v;
-                    if (idx < (uint32_t)kScratchVals) v = lds_u16(scratch + idx * 2u);
-                    else v = __ldg(p.vals + (b0 >> 1) + idx);
-                    ++idx;
-                    const uint32_t col = (uint32_t)wd * 32u + j;
-                    sts_u16(brow + ((col << 1) ^ (r7 << 4)), v);
+                for (int wd = 0; wd < 2; ++wd) {
+                    uint32_t rm = __brev(wd ? pw.w : pw.z);      // msb-first: clz gives the lowest column
+                    const uint32_t k1 = (r7 << 4) ^ (uint32_t)(wd * 64);
+                    while (rm) {
+                        const uint32_t j = (uint32_t)__clz(rm);
+                        rm &= ~(0x80000000u >> j);
+                        const uint16_t v = lds_u16(sa);
+                        sa += 2u;
+                        sts_u16(brow | ((j + j) ^ k1), v);
+                    }
+                }
+            } else {                                               // rare: very dense chunk, tail read from global
+                uint32_t idx = idx0;
+#pragma unroll
+                for (int wd = 0; wd < 2; ++wd) {
+                    uint32_t mk = wd ? pw.w : pw.z;
+                    while (mk) {
+                        const uint32_t j = (uint32_t)__ffs(mk) - 1u;
+                        mk &= mk - 1u;
+                        uint16_t v;
+                        if (idx < (uint32_t)kScratchVals) v = lds_u16(scratch + idx * 2u);
+                        else v = __ldg(p.vals + (b0 >> 1) + idx);
+                        ++idx;
+                        const uint32_t col = (uint32_t)wd * 32u + j;
+                        sts_u16(brow + ((col << 1) ^ (r7 << 4)), v);
+                    }
                 }
             }
             fence_proxy_async();
             mbar_arrive(full_b(s));
-            if (++s == kStages) { s = 0; ph ^= 1u; }
+            s += kTeams;
+            if (s >= kStages) { s -= kStages; ph ^= 1u; }
         }
     } else {
         // ===== epilogue: TMEM -> registers -> (+bias) -> 16-bit -> global =====
