@@ -135,7 +135,8 @@ PBL_API int pbl_linear_forward_host(const pbl_layer* layer, const void* x_host, 
                             void* stream);
 
 /* Which kernel pbl_linear_forward would launch for this (layer, M): 0 = CUDA-core bit-plane
- * GEMV/skinny kernel, 1 = tcgen05 bit-plane GEMM.  PBL_FORCE_KERNEL=0|1 overrides (tests). */
+ * kernel (fp32 I/O), 1 = tcgen05 bit-plane GEMM (M above PBL_SKINNY_MAX_M, default 16),
+ * 2 = mma.sync bit-plane skinny kernel (decode).  PBL_FORCE_KERNEL=0|1|2 overrides (tests). */
 PBL_API int pbl_select_kernel(const pbl_layer* layer, int64_t M);
 
 /* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */

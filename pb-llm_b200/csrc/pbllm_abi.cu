@@ -172,19 +172,23 @@ static int forced_kernel() {
     return atoi(e);
 }
 
-static int gemv_max_m() {
-    const char* e = getenv("PBL_GEMV_MAX_M");
+static int skinny_max_m() {
+    const char* e = getenv("PBL_SKINNY_MAX_M");
     if (e && *e) return atoi(e);
-    return 8;
+    return 16;
 }
 
+// 0 = CUDA-core bit-plane kernel, 1 = tcgen05 GEMM, 2 = mma.sync skinny kernel; -1 = forced kernel unsupported
 static int select_impl(const Layer& L, const void* x, int64_t ldx, const void* y, int64_t ldy, int64_t M) {
     const bool tc_ok = gemm_tc_supported(L, x, ldx, y, ldy, M);
+    const bool sk_ok = skinny_supported(L, M);
     const int f = forced_kernel();
     if (f == 0) return 0;
     if (f == 1) return tc_ok ? 1 : -1;
-    if (!tc_ok) return 0;
-    return (M <= gemv_max_m()) ? 0 : 1;
+    if (f == 2) return sk_ok ? 2 : -1;
+    if (!sk_ok) return 0;                       // fp32 I/O: CUDA cores
+    if (M <= skinny_max_m() || !tc_ok) return 2;
+    return 1;
 }
 
 int pbl_select_kernel(const pbl_layer* layer, int64_t M) {
@@ -208,8 +212,9 @@ int pbl_linear_forward(const pbl_layer* layer, const void* x, int64_t ldx, void*
     int rc = device_check_impl();
     if (rc) return rc;
     const int k = select_impl(L, x, ldx, y, ldy, M);
-    if (k < 0) { set_error("PBL_FORCE_KERNEL=1 but the tcgen05 path does not support this call"); return PBL_ERR_UNSUPPORTED; }
+    if (k < 0) { set_error("PBL_FORCE_KERNEL names a kernel that does not support this call"); return PBL_ERR_UNSUPPORTED; }
     if (k == 1) return launch_gemm_tc(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
+    if (k == 2) return launch_skinny(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
     return launch_gemv(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
 }
 

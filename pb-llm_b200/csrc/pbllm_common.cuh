@@ -63,5 +63,7 @@ int launch_unpack(const Layer& L, void* w_out, int64_t ldw, cudaStream_t s);
 int launch_gemv(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s);
 int launch_gemm_tc(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s);
 bool gemm_tc_supported(const Layer& L, const void* x, int64_t ldx, const void* y, int64_t ldy, int64_t M);
+int launch_skinny(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s);
+bool skinny_supported(const Layer& L, int64_t M);
 
 }  // namespace pbl

@@ -45,6 +45,15 @@ def rms_rel(y, ref):
     return float(np.sqrt(((y - ref) ** 2).mean()) / max(np.sqrt((ref ** 2).mean()), 1e-30))
 
 
+def forced(p, x, kernel):
+    """Run p.forward with PBL_FORCE_KERNEL=kernel (0 CUDA cores, 1 tcgen05 GEMM, 2 mma.sync skinny)."""
+    os.environ["PBL_FORCE_KERNEL"] = str(kernel)
+    try:
+        return p.forward(x)
+    finally:
+        os.environ.pop("PBL_FORCE_KERNEL", None)
+
+
 def rounded(a, dtype):
     """numpy fp32 array holding dtype-representable values (what the device tensor really holds)."""
     return torch.from_numpy(np.ascontiguousarray(a)).to(dtype).float().numpy()
@@ -179,19 +188,40 @@ def test_gemm_tc_matches_oracle(dtype, N, K, gs, M, bias):
     b = rounded(np.random.RandomState(2).standard_normal(N).astype(np.float32) * 0.1, dtype) if bias else None
     x = rounded(make_x(N * 3 + M, (M, K)), dtype)
     p = pb.PackedLinear.from_dense(t(w, dtype), None if b is None else t(b, dtype), t(low), gs)
-    assert p.select_kernel(M) == 1                                  # tcgen05 path is the one selected
-    y = p.forward(t(x, dtype))
+    assert p.select_kernel(M) == (1 if M > 16 else 2)               # tcgen05 above the skinny threshold
+    y = forced(p, t(x, dtype), 1)
     if M * N * K <= 4e8:
         ref = orc.linear(x, w, b)                                   # CPU oracle (double accumulate)
     else:                                                           # large: fp64 on device over the same w_sim
         ref = (t(x).double() @ t(w).double().t() + (0 if b is None else t(b).double())).cpu().numpy()
     assert relmax(y, ref) <= TOL[dtype], (relmax(y, ref), rms_rel(y, ref))
     assert rms_rel(y, ref) <= TOL[dtype]
-    os.environ["PBL_FORCE_KERNEL"] = "0"                            # both kernels agree on the same packed layer
-    try:
-        y0 = p.forward(t(x, dtype))
-    finally:
-        os.environ.pop("PBL_FORCE_KERNEL")
+    y0 = forced(p, t(x, dtype), 0)                                  # all kernels agree on the same packed layer
+    assert relmax(y, y0.float().cpu().numpy()) <= 2 * TOL[dtype]
+    if M <= 300:
+        y2 = forced(p, t(x, dtype), 2)
+        assert relmax(y2, ref) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N,K,gs,M,bias", [(128, 64, -1, 1, False), (96, 160, -1, 3, True), (100, 70, -1, 5, False),
+                                           (300, 520, -1, 8, True), (256, 512, 128, 2, False), (768, 768, -1, 1, True),
+                                           (33, 2048, -1, 9, False), (512, 1024, 256, 16, True), (4096, 4096, -1, 8, False),
+                                           (1024, 11008, -1, 7, False), (264, 1030, -1, 17, True)])
+def test_skinny_mma_matches_oracle(dtype, N, K, gs, M, bias):
+    """mma.sync bit-plane kernel (decode regime), incl. ragged N/K, odd leading dims, groups."""
+    w, low = synth_wsim(N, K, gs, dtype, seed=N + K + M)
+    b = rounded(np.random.RandomState(3).standard_normal(N).astype(np.float32) * 0.1, dtype) if bias else None
+    x = rounded(make_x(N * 5 + M, (M, K)), dtype)
+    p = pb.PackedLinear.from_dense(t(w, dtype), None if b is None else t(b, dtype), t(low), gs)
+    assert p.select_kernel(min(M, 16)) == 2
+    y = forced(p, t(x, dtype), 2)
+    ref = orc.linear(x, w, b) if M * N * K <= 4e8 else \
+        (t(x).double() @ t(w).double().t() + (0 if b is None else t(b).double())).cpu().numpy()
+    assert relmax(y, ref) <= TOL[dtype], (relmax(y, ref), rms_rel(y, ref))
+    assert rms_rel(y, ref) <= TOL[dtype]
+    assert torch.equal(y, forced(p, t(x, dtype), 2))                # deterministic reduction
+    y0 = forced(p, t(x, dtype), 0)
     assert relmax(y, y0.float().cpu().numpy()) <= 2 * TOL[dtype]
 
 
@@ -202,6 +232,8 @@ def test_gemm_tc_one_hot_activations_reproduce_w_sim_exactly():
     y = p.forward(torch.eye(256, device=DEV, dtype=torch.float16))
     assert p.select_kernel(256) == 1
     assert torch.equal(y, t(w, torch.float16).t())
+    y2 = forced(p, torch.eye(256, device=DEV, dtype=torch.float16), 2)   # register-built fragments: same exact tile
+    assert torch.equal(y2, t(w, torch.float16).t())
 
 
 # ---- golden fixtures from the executed reference --------------------------------------------------
