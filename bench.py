@@ -298,7 +298,7 @@ def main():
     if per:
         ach = flops / (kern_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"],
-                    "traffic": None, "kernel": "pbl tcgen05 bit-plane GEMM" if kernel_id == 1 else "pbl bit-plane skinny kernel (CUDA cores)",
+                    "traffic": None, "kernel": {0: "pbl CUDA-core bit-plane kernel", 1: "pbl tcgen05 bit-plane GEMM", 2: "pbl mma.sync bit-plane skinny kernel"}[kernel_id],
                     "launches": len(per), "avg_launch_ms": kern_ms / len(per), "peak_source": pk["src"] + ", sustained bf16",
                     "frac_of_burst_peak": ach / pk["tf_burst"],
                     "algorithmic_flops_per_launch": "2*M*N*K (M=tokens/step, N,K of the linear)"}
@@ -333,15 +333,27 @@ def main():
                 for i, p in enumerate(row):
                     p.forward(xd_in[SHAPES[i][3]], out=douts[i])
 
-        ms_d, _ = timed(dstep, 20, 3)
+        ms_d_eager, _ = timed(dstep, 20, 3)
+        # the decode step is launch-bound from Python (224 kernels of a few microseconds): replay it as a CUDA graph
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            dstep()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph, stream=side):
+                dstep()
+        ms_d, _ = timed(graph.replay, 50, 5)
         G = 1
         b_bin = nk / 8 + 4 * sum(p.N for row in layers for p in row) * G + 2 * Md * sum(p.K + p.N for row in layers for p in row)
         b_sal = 2 * nnz + sum(p.N + 1 for row in layers for p in row)
         ach = (b_bin + b_sal) / (ms_d * 1e-3) / 1e9
-        decode = {"tokens_per_s": Md * (1 if rowshard else world) / (ms_d * 1e-3), "ms_per_step": ms_d, "batch": Md,
+        decode = {"tokens_per_s": Md * (1 if rowshard else world) / (ms_d * 1e-3), "ms_per_step": ms_d,
+                  "ms_per_step_eager_python_launch": ms_d_eager, "batch": Md, "launch": "CUDA graph replay of the 224 launches",
+                  "kernel": "pbl mma.sync bit-plane skinny kernel" if layers[0][0].select_kernel(Md) == 2 else "pbl CUDA-core bit-plane kernel",
                   "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                                "traffic": None, "algorithmic_bytes_per_step": b_bin + b_sal,
-                               "actual_packed_bytes": packed_bytes, "peak_source": pk["src"]}}
+                               "actual_packed_bytes": packed_bytes, "actual_bytes_gbs": packed_bytes / (ms_d * 1e-3) / 1e9,
+                               "peak_source": pk["src"]}}
 
     stop.set()
     cb = None

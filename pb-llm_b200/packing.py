@@ -30,6 +30,7 @@ class PackedLinear:
 
     def __init__(self):
         self.handle = None
+        self._fwd = None
 
     @classmethod
     def from_dense(cls, w_sim: torch.Tensor, bias: Optional[torch.Tensor] = None,
@@ -118,18 +119,28 @@ class PackedLinear:
             raise RuntimeError(f"activation dtype {x.dtype} != packed weight dtype {self.dtype}")
         if x.shape[-1] != self.K:
             raise RuntimeError(f"last dim of x is {x.shape[-1]}, expected in_features={self.K}")
-        lead = x.shape[:-1]
-        x2 = x.reshape(-1, self.K)
+        x2 = x if x.dim() == 2 else x.reshape(-1, self.K)
         if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < self.K):
             x2 = x2.contiguous()
         M = x2.shape[0]
         y = out if out is not None else torch.empty((M, self.N), dtype=self.dtype, device=x.device)
         if M:
-            with torch.cuda.device(x.device):
-                rc = _lib.load().pbl_linear_forward(self.handle, C.c_void_p(x2.data_ptr()), x2.stride(0) if M > 1 else self.K,
-                                                    C.c_void_p(y.data_ptr()), y.stride(0), M, _stream(x.device))
-            _lib.check(rc, "pbl_linear_forward")
-        return y.view(*lead, self.N) if out is None else y
+            fwd = self._fwd
+            if fwd is None:
+                fwd = self._fwd = _lib.load().pbl_linear_forward
+            dev = x.device
+            if dev.index != torch.cuda.current_device():
+                with torch.cuda.device(dev):
+                    rc = fwd(self.handle, x2.data_ptr(), x2.stride(0) if M > 1 else self.K, y.data_ptr(), y.stride(0), M,
+                             torch.cuda.current_stream(dev).cuda_stream)
+            else:
+                rc = fwd(self.handle, x2.data_ptr(), x2.stride(0) if M > 1 else self.K, y.data_ptr(), y.stride(0), M,
+                         torch.cuda.current_stream(dev).cuda_stream)
+            if rc:
+                _lib.check(rc, "pbl_linear_forward")
+        if out is not None:
+            return y
+        return y if x.dim() == 2 else y.view(*x.shape[:-1], self.N)
 
     def forward_host(self, x_host: torch.Tensor, y_host: torch.Tensor, workspace: torch.Tensor):
         """End-to-end form with HOST buffers (pbl_linear_forward_host): H2D, kernel, D2H, sync."""

@@ -22,6 +22,23 @@ for _ in range(reps):
     p.forward(x, out=out)
 e1.record()
 torch.cuda.synchronize()
+ms_eager = e0.elapsed_time(e1) / reps
+# CUDA-graph replay: GPU time without the Python launch overhead
+g = torch.cuda.CUDAGraph()
+st = torch.cuda.Stream()
+with torch.cuda.stream(st):
+    p.forward(x, out=out)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g, stream=st):
+        for _ in range(reps):
+            p.forward(x, out=out)
+g.replay()
+torch.cuda.synchronize()
+e0.record()
+g.replay()
+e1.record()
+torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
+print(f"eager {ms_eager:.4f} ms/call;", end=" ")
 print(f"M={M} N={N} K={K} kernel={p.select_kernel(M)} {ms:.4f} ms {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s "
       f"packed {p.packed_bytes() / 1e6:.1f} MB -> {p.packed_bytes() / ms / 1e6:.1f} GB/s")
