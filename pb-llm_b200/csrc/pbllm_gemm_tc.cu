@@ -160,6 +160,7 @@ struct GemmParams {
     int M, N, K;
     int tiles_r, tiles_c, groups, tiles_per_group;
     int m_tiles, n_tiles, kblocks;
+    int bm;  // tokens per CTA tile: 256 (two UMMA halves) or 128 (one half; more CTAs when M is small)
 };
 
 template <typename T>
@@ -210,10 +211,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
             uint32_t ph = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int t = blockIdx.x + ti * gridDim.x;
-                const int m0 = (t / p.n_tiles) * BM;
+                const int m0 = (t / p.n_tiles) * p.bm;
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(empty(s), ph ^ 1u);
-                    mbar_arrive_expect_tx(full_a(s), kAStage);
+                    mbar_arrive_expect_tx(full_a(s), (uint32_t)p.bm * 128u);
                     tma_load_2d(smem_base + kOffA + s * kAStage, &tmap_x, kb * BK, m0, full_a(s));
                     if (++s == kStages) { s = 0; ph ^= 1u; }
                 }
@@ -228,8 +229,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
         uint32_t ph = 0, acc_ph = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int t = blockIdx.x + ti * gridDim.x;
-            const int m0 = (t / p.n_tiles) * BM;
-            const int halves = (m0 + 128 < p.M) ? 2 : 1;
+            const int m0 = (t / p.n_tiles) * p.bm;
+            const int halves = (p.bm == 256 && m0 + 128 < p.M) ? 2 : 1;
             mbar_wait(tmem_empty, acc_ph ^ 1u);
             tc_fence_after();
             for (int kb = 0; kb < KB; ++kb) {
@@ -408,8 +409,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
         T* y = reinterpret_cast<T*>(p.y);
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int t = blockIdx.x + ti * gridDim.x;
-            const int m0 = (t / p.n_tiles) * BM, n0 = (t % p.n_tiles) * BN;
-            const int halves = (m0 + 128 < p.M) ? 2 : 1;
+            const int m0 = (t / p.n_tiles) * p.bm, n0 = (t % p.n_tiles) * BN;
+            const int halves = (p.bm == 256 && m0 + 128 < p.M) ? 2 : 1;
             mbar_wait(tmem_full, acc_ph);
             tc_fence_after();
             for (int h = 0; h < halves; ++h) {
@@ -493,10 +494,20 @@ bool gemm_tc_supported(const Layer& L, const void* x, int64_t ldx, const void* y
 int launch_gemm_tc(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled driver entry point unavailable"); return PBL_ERR_CUDA; }
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int n_tiles = (int)((L.N + tc::BN - 1) / tc::BN);
+    // 256-token tiles amortise the weight expansion over two MMA halves; when that leaves SMs idle
+    // (small M), fall back to 128-token tiles to double the CTA count.
+    const int bm = (M <= 128 || ((M + 255) / 256) * (int64_t)n_tiles < num_sms) ? 128 : 256;
     CUtensorMap tmap;
     const cuuint64_t gdim[2] = {(cuuint64_t)L.K, (cuuint64_t)M};
     const cuuint64_t gstr[1] = {(cuuint64_t)ldx * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BM};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)bm};
     const cuuint32_t estr[2] = {1, 1};
     CUresult cr = enc(&tmap, L.dtype == PBL_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                       const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -507,17 +518,12 @@ int launch_gemm_tc(const Layer& L, const void* x, int64_t ldx, void* y, int64_t 
     p.planes = L.planes; p.vptr = L.vptr; p.vals = reinterpret_cast<const uint16_t*>(L.vals); p.affine = L.affine;
     p.bias = L.bias; p.y = y; p.ldy = ldy; p.M = (int)M; p.N = (int)L.N; p.K = (int)L.K;
     p.tiles_r = (int)L.tiles_r; p.tiles_c = (int)L.tiles_c; p.groups = (int)L.groups; p.tiles_per_group = L.tiles_per_group;
-    p.m_tiles = (int)((M + tc::BM - 1) / tc::BM);
-    p.n_tiles = (int)((L.N + tc::BN - 1) / tc::BN);
+    p.bm = bm;
+    p.m_tiles = (int)((M + bm - 1) / bm);
+    p.n_tiles = n_tiles;
     p.kblocks = (int)L.tiles_c;
 
-    static int num_sms = 0;
     static bool attr_set[2] = {false, false};
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
     const int which = L.dtype == PBL_F16 ? 0 : 1;
     auto kern = which == 0 ? gemm_tc_kernel<__half> : gemm_tc_kernel<__nv_bfloat16>;
     if (!attr_set[which]) {

@@ -228,16 +228,9 @@ skinny_mma_kernel(const uint4* __restrict__ planes, const uint32_t* __restrict__
         // ---- salient part: lane = row, (v - lo) * x over the row's salient columns -----------------------
         {
             const uint32_t b0 = (cs * 2u) & ~15u;
-            uint32_t idx = (cs - (b0 >> 1)) + warp_excl_scan(__popc(pw.z) + __popc(pw.w), lane);
+            const uint32_t idx0 = (cs - (b0 >> 1)) + warp_excl_scan(__popc(pw.z) + __popc(pw.w), lane);
             uint32_t rm0 = __brev(pw.z), rm1 = __brev(pw.w);
-            while (rm0 | rm1) {
-                uint32_t j;
-                if (rm0) { j = (uint32_t)__clz(rm0); rm0 &= ~(0x80000000u >> j); }
-                else { j = (uint32_t)__clz(rm1); rm1 &= ~(0x80000000u >> j); j += 32u; }
-                uint16_t v16;
-                if (idx < 512u) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v16) : "r"(scr + idx * 2u) : "memory");
-                else v16 = __ldg(vals + (b0 >> 1) + idx);
-                ++idx;
+            auto fma8 = [&](uint32_t j, uint16_t v16) {
                 const float c = sk_val<T>(v16) - my_lo;
                 const float4 xa = *reinterpret_cast<const float4*>(xt + j * kTok);
                 const float4 xb = *reinterpret_cast<const float4*>(xt + j * kTok + 4);
@@ -245,6 +238,30 @@ skinny_mma_kernel(const uint4* __restrict__ planes, const uint32_t* __restrict__
                 sacc[2] = fmaf(c, xa.z, sacc[2]); sacc[3] = fmaf(c, xa.w, sacc[3]);
                 sacc[4] = fmaf(c, xb.x, sacc[4]); sacc[5] = fmaf(c, xb.y, sacc[5]);
                 sacc[6] = fmaf(c, xb.z, sacc[6]); sacc[7] = fmaf(c, xb.w, sacc[7]);
+            };
+            if (ce - (b0 >> 1) <= 512u) {            // warp-uniform: the whole chunk is staged in shared memory
+                uint32_t sa = scr + idx0 * 2u;
+                while (rm0 | rm1) {
+                    uint32_t j;
+                    if (rm0) { j = (uint32_t)__clz(rm0); rm0 &= ~(0x80000000u >> j); }
+                    else { j = (uint32_t)__clz(rm1); rm1 &= ~(0x80000000u >> j); j += 32u; }
+                    uint16_t v16;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v16) : "r"(sa) : "memory");
+                    sa += 2u;
+                    fma8(j, v16);
+                }
+            } else {                                   // rare: very dense chunk, tail read from global
+                uint32_t idx = idx0;
+                while (rm0 | rm1) {
+                    uint32_t j;
+                    if (rm0) { j = (uint32_t)__clz(rm0); rm0 &= ~(0x80000000u >> j); }
+                    else { j = (uint32_t)__clz(rm1); rm1 &= ~(0x80000000u >> j); j += 32u; }
+                    uint16_t v16;
+                    if (idx < 512u) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v16) : "r"(scr + idx * 2u) : "memory");
+                    else v16 = __ldg(vals + (b0 >> 1) + idx);
+                    ++idx;
+                    fma8(j, v16);
+                }
             }
         }
     }

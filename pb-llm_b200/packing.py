@@ -105,6 +105,14 @@ class PackedLinear:
         _lib.check(_lib.load().pbl_layer_create(C.byref(d), C.byref(h)), "pbl_layer_create")
         self.handle = h
 
+    def __deepcopy__(self, memo):
+        b = None if self.bias is None else self.bias.clone()
+        return PackedLinear.from_buffers(self.N, self.K, self.groupsize, self.dtype, self.planes.clone(), self.vptr.clone(),
+                                         self.vals.clone(), self.affine.clone(), b)
+
+    def __getstate__(self):
+        raise RuntimeError("PackedLinear holds a native handle; save its buffers() and rebuild with from_buffers()")
+
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None
         if h is not None and _lib._lib is not None:
