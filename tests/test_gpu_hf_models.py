@@ -38,17 +38,30 @@ def test_hf_model_drop_in(make, method):
     n_q = sum(isinstance(m, pb.BinaryInterface) for m in model.modules())
     assert n_q >= 2 * 6 + 1                                 # every nn.Linear incl. lm_head (tied or not)
     ids = torch.randint(0, 512, (2, 64), device=DEV)
+    layer_err = []
+
+    def hook(mod, inp, out):      # every packed module against F.linear over its own effective weight, fp32
+        x, w = inp[0], mod.dense_weight()
+        ref = torch.nn.functional.linear(x.float(), w.float(), None if mod.bias is None else mod.bias.float())
+        layer_err.append(float((out.float() - ref).abs().max() / ref.abs().max().clamp_min(1e-9)))
+
+    hooks = [m.register_forward_hook(hook) for m in model.modules() if isinstance(m, pb.BinaryInterface)]
     with torch.no_grad():
         logits = model(ids).logits                          # M = 128 tokens: tcgen05 path
         short = model(ids[:, :3]).logits                    # M = 6 tokens: mma.sync skinny path
+    for h in hooks:
+        h.remove()
+    assert len(layer_err) == 2 * n_q and max(layer_err) <= 1e-3, max(layer_err)   # the parity bar, layer by layer
+    with torch.no_grad():
         dense = copy.deepcopy(model)
-        pb.to_regular_linear(dense)                         # reference's simulated-quant model
+        pb.to_regular_linear(dense)                         # reference's simulated-quant model (cuBLAS fp16 GEMMs)
         assert not any(isinstance(m, pb.BinaryInterface) for m in dense.modules())
         ref = dense(ids).logits
         ref_short = dense(ids[:, :3]).logits
-    scale = ref.float().abs().max()
-    assert ((logits.float() - ref.float()).abs().max() / scale) < 5e-3     # fp16 model, 2 layers of accumulation
-    assert ((short.float() - ref_short.float()).abs().max() / ref_short.float().abs().max()) < 5e-3
+    # logit level: a random-init tiny model amplifies the per-layer fp16 rounding differences between two
+    # correct fp32-accumulate implementations (LayerNorm / softmax over 3 tokens), so this bound is a sanity check
+    assert ((logits.float() - ref.float()).abs().max() / ref.float().abs().max()) < 5e-2
+    assert ((short.float() - ref_short.float()).abs().max() / ref_short.float().abs().max()) < 5e-2
     assert pb.pack_model(model, keep_latent=False) == n_q  # free the latent weights, serve from packed form only
     with torch.no_grad():
         again = model(ids).logits
