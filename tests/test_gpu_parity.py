@@ -225,6 +225,32 @@ def test_skinny_mma_matches_oracle(dtype, N, K, gs, M, bias):
     assert relmax(y, y0.float().cpu().numpy()) <= 2 * TOL[dtype]
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N,K,gs,M,bias", [(256, 64, -1, 16, False), (256, 256, -1, 300, True), (264, 520, -1, 700, True),
+                                           (768, 768, -1, 1000, True), (512, 1024, 256, 513, False),
+                                           (1024, 4096, -1, 2048, False), (4096, 4096, -1, 2560, False)])
+def test_gemm_tc_cta_pair_matches_oracle(dtype, N, K, gs, M, bias):
+    """cta_group::2 kernel (SM pairs), forced on for every shape incl. ragged M/N/K and single-CTA-valid tiles."""
+    w, low = synth_wsim(N, K, gs, dtype, seed=N + K + M)
+    b = rounded(np.random.RandomState(4).standard_normal(N).astype(np.float32) * 0.1, dtype) if bias else None
+    x = rounded(make_x(N * 11 + M, (M, K)), dtype)
+    p = pb.PackedLinear.from_dense(t(w, dtype), None if b is None else t(b, dtype), t(low), gs)
+    os.environ["PBL_GEMM_2CTA"] = "2"
+    try:
+        y = forced(p, t(x, dtype), 1)
+    finally:
+        os.environ.pop("PBL_GEMM_2CTA")
+    ref = orc.linear(x, w, b) if M * N * K <= 4e8 else \
+        (t(x).double() @ t(w).double().t() + (0 if b is None else t(b).double())).cpu().numpy()
+    assert relmax(y, ref) <= TOL[dtype], (relmax(y, ref), rms_rel(y, ref))
+    os.environ["PBL_GEMM_2CTA"] = "0"
+    try:
+        y1 = forced(p, t(x, dtype), 1)
+    finally:
+        os.environ.pop("PBL_GEMM_2CTA")
+    assert torch.equal(y, y1)                                       # same tile, same k order: bit-identical to the 1-CTA kernel
+
+
 def test_gemm_tc_one_hot_activations_reproduce_w_sim_exactly():
     """x = I  =>  y = w_sim^T bit-for-bit: the expanded tile IS the reference's tensor."""
     w, low = synth_wsim(512, 256, -1, torch.float16, 77)
