@@ -1,16 +1,17 @@
 // Bit-plane skinny kernel on tensor cores (decode regime: M <= 8 tokens per pass), fp16 / bf16.
 //
-// Same math as gemv_kernel (y = x . w_sim^T + b from the packed form, fp32 accumulation) but the
-// dense {lo,hi} part no longer costs one CUDA-core op per weight per token:
-//   * dense part: the warp's 32x64 weight block is rebuilt IN REGISTERS as mma.sync m16n8k16 A
-//     fragments (bit -> PRMT byte-sign replicate -> LOP3 {lo,hi} select, ~1.25 ALU ops/weight for
-//     all 8 tokens at once) and multiplied with the activations as the 16x8 B operand; nothing
-//     of the weight tile ever touches shared memory.
-//   * salient part: lane = row walks its salient bits and accumulates (v - lo) * x[m] from an fp32
-//     transposed activation tile (one pair of LDS.128 gives all 8 tokens).
+// Same math as gemv_kernel (y = x . w_sim^T + b from the packed form, fp32 accumulation), organised
+// as a per-warp mini-GEMM: each warp rebuilds its 32x64 block of the EXACT fp16/bf16 w_sim tile in a
+// private 4 KB shared-memory buffer (bit -> PRMT byte-sign replicate -> LOP3 {lo,hi} select, 8
+// conflict-free STS.128 per row, then the row's salient values patched over their positions -- the
+// same expansion as the tcgen05 kernels, so the tile is bit-identical to theirs), reads it back as
+// mma.sync m16n8k16 A fragments with ldmatrix (XOR-swizzled rows, conflict-free) and multiplies with
+// the activations (B fragment, 8 tokens).  The salient entries therefore ride the tensor cores too:
+// no per-element FMA chain, cost independent of M <= 8.
 // HBM-bound target: the packed stream (planes 0.25 B/weight + values) is read exactly once.
 // CTA = one 32-row group x (up to) 8 tokens; kWarps warps split the k-blocks, deterministic
 // shared-memory reduction at the end.
+#include <cstdlib>
 #include <type_traits>
 
 #include "pbllm_common.cuh"
@@ -22,10 +23,10 @@ constexpr int kWarps = 16;
 constexpr int kTok = 8;                         // tokens per pass (mma N)
 constexpr int kXrStride = kTileCols + 8;        // halves per token row (+8: conflict-free B-fragment LDS)
 constexpr int kXrBytes = kTok * kXrStride * 2;  // 1152
-constexpr int kXtBytes = kTileCols * kTok * 4;  // 2048: fp32 [64 cols][8 tokens]
+constexpr int kTileBytes = kRgRows * kTileCols * 2;  // 4096: the warp's 32x64 16-bit weight tile (swizzled)
 constexpr int kScrBytes = 1024;                 // staged salient values (512 x 16 bit)
-constexpr int kWarpBytes = kXrBytes + kXtBytes + kScrBytes;  // 4224
-static_assert(kWarpBytes % 16 == 0, "alignment");
+constexpr int kWarpBytes = kTileBytes + kXrBytes + kScrBytes;  // 6272
+static_assert(kWarpBytes % 128 == 0, "alignment");
 }  // namespace sk
 
 __device__ __forceinline__ uint32_t sk_prmt(uint32_t a, uint32_t b, uint32_t sel) {
@@ -74,26 +75,25 @@ skinny_mma_kernel(const uint4* __restrict__ planes, const uint32_t* __restrict__
                   const float2* __restrict__ affine, const float* __restrict__ bias, const T* __restrict__ x, int64_t ldx,
                   T* __restrict__ y, int64_t ldy, int M, int N, int K, int tiles_c, int groups, int tiles_per_group) {
     using namespace sk;
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint8_t* wsm = smem + wid * kWarpBytes;
-    uint16_t* xr = reinterpret_cast<uint16_t*>(wsm);                       // [8][72] 16-bit
-    float* xt = reinterpret_cast<float*>(wsm + kXrBytes);                  // [64][8] fp32
-    const uint32_t scr = (uint32_t)__cvta_generic_to_shared(wsm + kXrBytes + kXtBytes);
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(wsm);                    // [32 rows][64] 16-bit, swizzled
+    uint16_t* xr = reinterpret_cast<uint16_t*>(wsm + kTileBytes);                       // [8][72] 16-bit
+    const uint32_t scr = (uint32_t)__cvta_generic_to_shared(wsm + kTileBytes + kXrBytes);
 
     const int rg = blockIdx.x;                   // global 32-row group
     const int tr = rg / kRgPerTile, rgi = rg % kRgPerTile;
-    const int row = rg * kRgRows + lane;         // lane's own row (salient part)
+    const int row = rg * kRgRows + lane;         // lane's own row (expansion: thread = weight row)
     const int m0 = blockIdx.y * kTok;
     const int g4 = lane >> 2, t4 = lane & 3;     // mma fragment coordinates
     const uint16_t* x16 = reinterpret_cast<const uint16_t*>(x);
+    const uint32_t r7 = (uint32_t)(lane & 7);
+    const uint32_t brow = tile_s + (uint32_t)lane * 128u;      // my row of the tile (128 B), chunks XOR-swizzled by r7
 
-    float cacc[2][4];                            // dense accumulators (two m16 tiles)
-    float sacc[kTok];                            // salient accumulators (lane = row)
+    float cacc[2][4];                            // accumulators (two m16 tiles x 8 tokens)
 #pragma unroll
     for (int i = 0; i < 4; ++i) cacc[0][i] = cacc[1][i] = 0.f;
-#pragma unroll
-    for (int m = 0; m < kTok; ++m) sacc[m] = 0.f;
 
     // ---- prefetch helpers -----------------------------------------------------------------------
     struct Meta { uint4 pw; uint32_t cs, ce; };
@@ -133,15 +133,29 @@ skinny_mma_kernel(const uint4* __restrict__ planes, const uint32_t* __restrict__
         }
     };
 
-    int cur_g = -1;
-    uint32_t LLa[2] = {0, 0}, DDa[2] = {0, 0}, LLb[2] = {0, 0}, DDb[2] = {0, 0};   // fragment rows g4 / g4+8 of each tile
-    float my_lo = 0.f;
+    // Programmatic dependent launch: let the next kernel in the stream start its own weight prefetch now;
+    // everything below up to griddepcontrol.wait touches only immutable packed weights.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
+    int cur_g = wid < tiles_c ? wid / tiles_per_group : 0;
+    float2 a_first = __ldg(affine + (int64_t)row * groups + cur_g);      // overlaps the meta / value loads
     Meta mt0 = load_meta(wid), mt1 = load_meta(wid + kWarps);
     uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
     uint32_t xv[kTok];
     load_vals(mt0, q0, q1);
+    uint32_t LL, DD;
+    {
+        const uint32_t lo = sk_bits16<T>(a_first.x), hi = sk_bits16<T>(a_first.y);
+        LL = lo | (lo << 16);
+        DD = (lo ^ hi) * 0x10001u;
+    }
+    // activations (and y) belong to the producer kernel: wait for it before the first read of x
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     load_x(wid, xv);
+
+    // ldmatrix source rows for this lane: matrix i = lane>>3 -> (row block i&1, k chunk i>>1)
+    const int lm_row = (lane & 7) + ((lane >> 3) & 1) * 8;      // row within a 16-row tile
+    const uint32_t lm_kc = (uint32_t)(lane >> 4);                // 0/1: which 8-column chunk of the k16 step
 
     for (int kb = wid; kb < tiles_c; kb += kWarps) {
         const uint4 pw = mt0.pw;
@@ -160,115 +174,102 @@ skinny_mma_kernel(const uint4* __restrict__ planes, const uint32_t* __restrict__
         const int g = kb / tiles_per_group;
         if (g != cur_g) {
             cur_g = g;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const float2 aa = __ldg(affine + (int64_t)(rg * kRgRows + 16 * h + g4) * groups + g);
-                const float2 ab = __ldg(affine + (int64_t)(rg * kRgRows + 16 * h + g4 + 8) * groups + g);
-                uint32_t lo = sk_bits16<T>(aa.x), hi = sk_bits16<T>(aa.y);
-                LLa[h] = lo | (lo << 16); DDa[h] = (lo ^ hi) * 0x10001u;
-                lo = sk_bits16<T>(ab.x); hi = sk_bits16<T>(ab.y);
-                LLb[h] = lo | (lo << 16); DDb[h] = (lo ^ hi) * 0x10001u;
-            }
-            my_lo = __ldg(affine + (int64_t)row * groups + g).x;
+            const float2 a = __ldg(affine + (int64_t)row * groups + g);
+            const uint32_t lo = sk_bits16<T>(a.x), hi = sk_bits16<T>(a.y);
+            LL = lo | (lo << 16);
+            DD = (lo ^ hi) * 0x10001u;
         }
 
-        // ---- stage activations (row layout for B fragments, fp32 transposed for the salient part)
-        //      and this row group's salient values
+        // ---- stage activations (row layout for the B fragments) and this row group's salient values
         __syncwarp();
+        const uint32_t b0 = (cs * 2u) & ~15u;
         {
-            float4 lo4a, lo4b, hi4a, hi4b;
-            float2 f;
 #pragma unroll
             for (int m = 0; m < kTok; ++m) *reinterpret_cast<uint32_t*>(xr + m * kXrStride + 2 * lane) = xc[m];
-            f = sk_unpack2<T>(xc[0]); lo4a.x = f.x; hi4a.x = f.y;
-            f = sk_unpack2<T>(xc[1]); lo4a.y = f.x; hi4a.y = f.y;
-            f = sk_unpack2<T>(xc[2]); lo4a.z = f.x; hi4a.z = f.y;
-            f = sk_unpack2<T>(xc[3]); lo4a.w = f.x; hi4a.w = f.y;
-            f = sk_unpack2<T>(xc[4]); lo4b.x = f.x; hi4b.x = f.y;
-            f = sk_unpack2<T>(xc[5]); lo4b.y = f.x; hi4b.y = f.y;
-            f = sk_unpack2<T>(xc[6]); lo4b.z = f.x; hi4b.z = f.y;
-            f = sk_unpack2<T>(xc[7]); lo4b.w = f.x; hi4b.w = f.y;
-            float4* dst = reinterpret_cast<float4*>(xt + (2 * lane) * kTok);
-            dst[0] = lo4a; dst[1] = lo4b; dst[2] = hi4a; dst[3] = hi4b;
-            const uint32_t b0 = (cs * 2u) & ~15u;
             const uint32_t o0 = 16u * lane, o1 = o0 + 512u;
             if (b0 + o0 < ce * 2u) asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(scr + o0), "r"(v0.x), "r"(v0.y), "r"(v0.z), "r"(v0.w) : "memory");
             if (b0 + o1 < ce * 2u) asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(scr + o1), "r"(v1.x), "r"(v1.y), "r"(v1.z), "r"(v1.w) : "memory");
         }
         __syncwarp();
 
-        // ---- dense part on tensor cores: A fragments from bits, B fragments from xr -------------------
-        uint32_t bfr[4][2];
+        // ---- rebuild my row (64 exact 16-bit values) in the warp's tile: dense {lo,hi} select ...
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            bfr[q][0] = *reinterpret_cast<const uint32_t*>(xr + g4 * kXrStride + 16 * q + 2 * t4);
-            bfr[q][1] = *reinterpret_cast<const uint32_t*>(xr + g4 * kXrStride + 16 * q + 2 * t4 + 8);
-        }
-        const uint32_t sh7 = 7u - 2u * t4, sh6 = 6u - 2u * t4;
+        for (int wd = 0; wd < 2; ++wd) {
+            const uint32_t sg = wd ? pw.y : pw.x;
+            const uint32_t X0 = sg, X1 = sg << 1, X2 = sg << 2, X3 = sg << 3, X4 = sg << 4, X5 = sg << 5, X6 = sg << 6,
+                           X7 = sg << 7;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int ra = 16 * h + g4, rb = ra + 8;
-#pragma unroll
-            for (int wd = 0; wd < 2; ++wd) {
-                const uint32_t own = wd ? pw.y : pw.x;
-                const uint32_t sa = __shfl_sync(0xffffffffu, own, ra), sb = __shfl_sync(0xffffffffu, own, rb);
-                const uint32_t a7 = sa << sh7, a6 = sa << sh6, b7 = sb << sh7, b6 = sb << sh6;
-                uint32_t fa[4], fb[4];
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const uint32_t sel = 0x8888u | (uint32_t)b | ((uint32_t)b << 4) | ((uint32_t)(4 + b) << 8) | ((uint32_t)(4 + b) << 12);
-                    fa[b] = sk_sel(LLa[h], DDa[h], sk_prmt(a7, a6, sel));
-                    fb[b] = sk_sel(LLb[h], DDb[h], sk_prmt(b7, b6, sel));
-                }
-                mma_16816<T>(cacc[h], fa[0], fb[0], fa[1], fb[1], bfr[2 * wd][0], bfr[2 * wd][1]);
-                mma_16816<T>(cacc[h], fa[2], fb[2], fa[3], fb[3], bfr[2 * wd + 1][0], bfr[2 * wd + 1][1]);
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t sel = 0x8888u | (uint32_t)c | ((uint32_t)c << 4) | ((uint32_t)(4 + c) << 8) | ((uint32_t)(4 + c) << 12);
+                const uint32_t h0 = sk_sel(LL, DD, sk_prmt(X7, X6, sel));
+                const uint32_t h1 = sk_sel(LL, DD, sk_prmt(X5, X4, sel));
+                const uint32_t h2 = sk_sel(LL, DD, sk_prmt(X3, X2, sel));
+                const uint32_t h3 = sk_sel(LL, DD, sk_prmt(X1, X0, sel));
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(brow + ((((uint32_t)(wd * 4 + c)) ^ r7) << 4)), "r"(h0), "r"(h1),
+                             "r"(h2), "r"(h3)
+                             : "memory");
             }
         }
-
-        // ---- salient part: lane = row, (v - lo) * x over the row's salient columns -----------------------
+        // ... then patch the salient values over their positions
         {
-            const uint32_t b0 = (cs * 2u) & ~15u;
             const uint32_t idx0 = (cs - (b0 >> 1)) + warp_excl_scan(__popc(pw.z) + __popc(pw.w), lane);
-            uint32_t rm0 = __brev(pw.z), rm1 = __brev(pw.w);
-            auto fma8 = [&](uint32_t j, uint16_t v16) {
-                const float c = sk_val<T>(v16) - my_lo;
-                const float4 xa = *reinterpret_cast<const float4*>(xt + j * kTok);
-                const float4 xb = *reinterpret_cast<const float4*>(xt + j * kTok + 4);
-                sacc[0] = fmaf(c, xa.x, sacc[0]); sacc[1] = fmaf(c, xa.y, sacc[1]);
-                sacc[2] = fmaf(c, xa.z, sacc[2]); sacc[3] = fmaf(c, xa.w, sacc[3]);
-                sacc[4] = fmaf(c, xb.x, sacc[4]); sacc[5] = fmaf(c, xb.y, sacc[5]);
-                sacc[6] = fmaf(c, xb.z, sacc[6]); sacc[7] = fmaf(c, xb.w, sacc[7]);
-            };
             if (ce - (b0 >> 1) <= 512u) {            // warp-uniform: the whole chunk is staged in shared memory
                 uint32_t sa = scr + idx0 * 2u;
-                while (rm0 | rm1) {
-                    uint32_t j;
-                    if (rm0) { j = (uint32_t)__clz(rm0); rm0 &= ~(0x80000000u >> j); }
-                    else { j = (uint32_t)__clz(rm1); rm1 &= ~(0x80000000u >> j); j += 32u; }
-                    uint16_t v16;
-                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v16) : "r"(sa) : "memory");
-                    sa += 2u;
-                    fma8(j, v16);
+#pragma unroll
+                for (int wd = 0; wd < 2; ++wd) {
+                    uint32_t rm = __brev(wd ? pw.w : pw.z);
+                    const uint32_t k1 = (r7 << 4) ^ (uint32_t)(wd * 64);
+                    while (rm) {
+                        const uint32_t j = (uint32_t)__clz(rm);
+                        rm &= ~(0x80000000u >> j);
+                        uint16_t v16;
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v16) : "r"(sa) : "memory");
+                        sa += 2u;
+                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(brow | ((j + j) ^ k1)), "h"(v16) : "memory");
+                    }
                 }
             } else {                                   // rare: very dense chunk, tail read from global
                 uint32_t idx = idx0;
-                while (rm0 | rm1) {
-                    uint32_t j;
-                    if (rm0) { j = (uint32_t)__clz(rm0); rm0 &= ~(0x80000000u >> j); }
-                    else { j = (uint32_t)__clz(rm1); rm1 &= ~(0x80000000u >> j); j += 32u; }
-                    uint16_t v16;
-                    if (idx < 512u) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v16) : "r"(scr + idx * 2u) : "memory");
-                    else v16 = __ldg(vals + (b0 >> 1) + idx);
-                    ++idx;
-                    fma8(j, v16);
+#pragma unroll
+                for (int wd = 0; wd < 2; ++wd) {
+                    uint32_t mk = wd ? pw.w : pw.z;
+                    while (mk) {
+                        const uint32_t j = (uint32_t)__ffs(mk) - 1u;
+                        mk &= mk - 1u;
+                        uint16_t v16;
+                        if (idx < 512u) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v16) : "r"(scr + idx * 2u) : "memory");
+                        else v16 = __ldg(vals + (b0 >> 1) + idx);
+                        ++idx;
+                        const uint32_t col = (uint32_t)wd * 32u + j;
+                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(brow + ((col << 1) ^ (r7 << 4))), "h"(v16) : "memory");
+                    }
                 }
+            }
+        }
+        __syncwarp();
+
+        // ---- tensor cores: A fragments by ldmatrix from the swizzled tile, B fragments from xr ------------
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t bq0 = *reinterpret_cast<const uint32_t*>(xr + g4 * kXrStride + 16 * q + 2 * t4);
+            const uint32_t bq1 = *reinterpret_cast<const uint32_t*>(xr + g4 * kXrStride + 16 * q + 2 * t4 + 8);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t rr = (uint32_t)(16 * h + lm_row);
+                const uint32_t addr = tile_s + rr * 128u + ((((uint32_t)(2 * q) + lm_kc) ^ (rr & 7u)) << 4);
+                uint32_t a0, a1, a2, a3;
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                             : "r"(addr)
+                             : "memory");
+                mma_16816<T>(cacc[h], a0, a1, a2, a3, bq0, bq1);
             }
         }
     }
 
-    // ---- combine dense fragments + salient partials per warp, then reduce across warps (split-K) ----
+    // ---- per-warp partials -> shared memory, then reduce across warps (split-K), add bias, store ----
     __syncwarp();
-    float* red = reinterpret_cast<float*>(wsm);   // [32 rows][8 tokens] fp32 = 1 KB, reuses the xr/xt area
+    float* red = reinterpret_cast<float*>(wsm);   // [32 rows][8 tokens] fp32 = 1 KB, reuses the tile area
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         red[(16 * h + g4) * kTok + 2 * t4] = cacc[h][0];
@@ -276,9 +277,6 @@ skinny_mma_kernel(const uint4* __restrict__ planes, const uint32_t* __restrict__
         red[(16 * h + g4 + 8) * kTok + 2 * t4] = cacc[h][2];
         red[(16 * h + g4 + 8) * kTok + 2 * t4 + 1] = cacc[h][3];
     }
-    __syncwarp();
-#pragma unroll
-    for (int m = 0; m < kTok; ++m) red[lane * kTok + m] += sacc[m];
     __syncthreads();
     if (threadIdx.x < 32 * kTok) {
         const int m = threadIdx.x >> 5, r = threadIdx.x & 31;
@@ -309,15 +307,31 @@ int launch_skinny(const Layer& L, const void* x, int64_t ldx, void* y, int64_t l
         if (rc) return rc;
         attr_set[which] = true;
     }
-    if (which == 0)
-        skinny_mma_kernel<__half><<<grid, sk::kWarps * 32, smem, s>>>(L.planes, L.vptr, (const uint16_t*)L.vals, L.affine, L.bias,
-                                                                     (const __half*)x, ldx, (__half*)y, ldy, (int)M, (int)L.N,
-                                                                     (int)L.K, (int)L.tiles_c, (int)L.groups, L.tiles_per_group);
-    else
-        skinny_mma_kernel<__nv_bfloat16><<<grid, sk::kWarps * 32, smem, s>>>(L.planes, L.vptr, (const uint16_t*)L.vals, L.affine,
-                                                                             L.bias, (const __nv_bfloat16*)x, ldx,
-                                                                             (__nv_bfloat16*)y, ldy, (int)M, (int)L.N, (int)L.K,
-                                                                             (int)L.tiles_c, (int)L.groups, L.tiles_per_group);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(sk::kWarps * 32);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static int pdl = -1;
+    if (pdl < 0) { const char* e = getenv("PBL_PDL"); pdl = (e && *e) ? atoi(e) : 1; }
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const uint16_t* vals16 = (const uint16_t*)L.vals;
+    const int Mi = (int)M, Ni = (int)L.N, Ki = (int)L.K, tci = (int)L.tiles_c, gi = (int)L.groups, tpg = L.tiles_per_group;
+    cudaError_t le;
+    if (which == 0) {
+        const __half* xx = (const __half*)x; __half* yy = (__half*)y;
+        le = cudaLaunchKernelEx(&cfg, skinny_mma_kernel<__half>, L.planes, L.vptr, vals16, L.affine, L.bias, xx, ldx, yy, ldy, Mi, Ni,
+                                Ki, tci, gi, tpg);
+    } else {
+        const __nv_bfloat16* xx = (const __nv_bfloat16*)x; __nv_bfloat16* yy = (__nv_bfloat16*)y;
+        le = cudaLaunchKernelEx(&cfg, skinny_mma_kernel<__nv_bfloat16>, L.planes, L.vptr, vals16, L.affine, L.bias, xx, ldx, yy, ldy,
+                                Mi, Ni, Ki, tci, gi, tpg);
+    }
+    if (le != cudaSuccess) { count_launch(); return check_cuda(le, "skinny launch"); }
     count_launch();
     return check_cuda(cudaGetLastError(), "skinny launch");
 }
