@@ -294,11 +294,16 @@ def main():
     flops = sum(2.0 * M * p.N * p.K for _, p in per)
     pk = peaks()
     kernel_id = layers[0][0].select_kernel(M)
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/
+    # r01_gemm_tc2_cta_pair_M16384_N4096_K4096.md): dram read 145.0 MB + write 95.8 MB for the
+    # q/k/v/o-shaped launch (algorithmic: 134 MB x + 134 MB y + 7.6 MB packed weights; part of y is
+    # still in L2 when the capture window closes).
+    ncu_traffic = {"launch": "M=16384 N=4096 K=4096", "bytes": 145.033216e6 + 95.770368e6, "algorithmic_bytes": 2 * 16384 * 4096 * 2 + 7.6e6}
     roofline = None
     if per:
         ach = flops / (kern_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"],
-                    "traffic": None, "kernel": {0: "pbl CUDA-core bit-plane kernel", 1: "pbl tcgen05 bit-plane GEMM", 2: "pbl mma.sync bit-plane skinny kernel"}[kernel_id],
+                    "traffic": ncu_traffic["bytes"] if (kernel_id == 1 and M >= 2048) else None, "traffic_note": ncu_traffic, "kernel": {0: "pbl CUDA-core bit-plane kernel", 1: "pbl tcgen05 bit-plane GEMM", 2: "pbl mma.sync bit-plane skinny kernel"}[kernel_id],
                     "launches": len(per), "avg_launch_ms": kern_ms / len(per), "peak_source": pk["src"] + ", sustained bf16",
                     "frac_of_burst_peak": ach / pk["tf_burst"],
                     "algorithmic_flops_per_launch": "2*M*N*K (M=tokens/step, N,K of the linear)"}
