@@ -360,6 +360,47 @@ def main():
                                "actual_packed_bytes": packed_bytes, "actual_bytes_gbs": packed_bytes / (ms_d * 1e-3) / 1e9,
                                "peak_source": pk["src"]}}
 
+    # -- the literal XNOR-popcount kernel (BiRealLinear format: alpha*sign(W), binarized activations) ---------------
+    xnor = None
+    if not args.no_decode and not rowshard:
+        Md = args.batch
+        blayers = []
+        for li in range(args.layers):
+            row = []
+            for si, (name, N, K, src) in enumerate(SHAPES):
+                gq = torch.Generator(device=dev).manual_seed(7000 * li + si)
+                w = torch.randn(N, K, device=dev, generator=gq)
+                row.append(pb.PackedLinear.from_dense((w.abs().mean(1, keepdim=True) * torch.sign(w)).half()))
+                del w
+            blayers.append(row)
+        xb_in = {k: v[:Md].contiguous() for k, v in xin.items()}
+        bouts = [torch.empty(Md, p.N, device=dev, dtype=torch.float32) for p in blayers[0]]
+        bws = torch.empty(max(p.bireal_workspace_bytes(Md) for p in blayers[0]), dtype=torch.uint8, device=dev)
+
+        def bstep():
+            for row in blayers:
+                for i, p in enumerate(row):
+                    p.bireal_forward(xb_in[SHAPES[i][3]], out=bouts[i], workspace=bws)
+
+        bgraph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            bstep()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(bgraph, stream=side):
+                bstep()
+        ms_b, _ = timed(bgraph.replay, 50, 5)
+        nb = sum(p.N for row in blayers for p in row)
+        kb_ = sum(p.K for row in blayers for p in row)
+        b_alg = nk / 8 + 8 * nb + Md * (2 * kb_ + 4 * nb)       # sign plane + {lo,hi} + fp16 x in + fp32 y out
+        ach = b_alg / (ms_b * 1e-3) / 1e9
+        xnor = {"what": "BiRealLinear forward (quant/quantizer.py:151-169) as XNOR-popcount over the packed sign plane, "
+                        "Llama-7B shapes, 224 launches + 224 activation-binarize launches per step, CUDA graph replay",
+                "tokens_per_s": Md * world / (ms_b * 1e-3), "ms_per_step": ms_b, "batch": Md,
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                             "traffic": None, "algorithmic_bytes_per_step": b_alg, "peak_source": pk["src"]}}
+        del blayers
+
     stop.set()
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -376,7 +417,7 @@ def main():
                            "packed_bytes": packed_bytes, "bits_per_weight": 8.0 * packed_bytes / nk * (world if rowshard else 1),
                            "salient_fraction": nnz / nk * (world if rowshard else 1), "model_build_s": build_s},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks_summary(samples), "roofline": roofline,
-                "cpu_baseline": cb, "decode": decode}
+                "cpu_baseline": cb, "decode": decode, "xnor_popcount": xnor}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PBL_ABI_VERSION 1
+#define PBL_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define PBL_API __attribute__((visibility("default")))
@@ -105,6 +105,8 @@ typedef struct {
     const void* vals;    /* device, dtype, 16 B aligned, >= nnz + 8 elements */
     const void* affine;  /* device float2 [n_pad][groups] */
     const void* bias;    /* device float32 [N] or NULL (bias added inside, as F.linear does) */
+    const void* sign_planes; /* optional, device uint2 [tiles_r][tiles_c][128] = the sign words of `planes` only;
+                              * may be given iff nnz == 0 (pure binary layer): halves the bytes pbl_bireal_forward streams */
 } pbl_layer_desc;
 
 typedef struct pbl_layer pbl_layer; /* opaque; borrows the descriptor's device pointers */
@@ -133,6 +135,16 @@ PBL_API int pbl_linear_forward(const pbl_layer* layer, const void* x, int64_t ld
 PBL_API size_t pbl_forward_host_workspace(const pbl_layer* layer, int64_t M);
 PBL_API int pbl_linear_forward_host(const pbl_layer* layer, const void* x_host, void* y_host, int64_t M, void* workspace,
                             void* stream);
+
+/* XNOR-popcount forward of BiRealLinear (quant/quantizer.py:151-169): activations are binarized too,
+ *   y[m][i] = sum_j sign(x[m][j]) * w_sim[i][j]        (fp32 out, NO bias -- the reference drops it, :168)
+ * evaluated as hi*(popc(b&xp)-popc(b&xn)) + lo*(popc(nb&xp)-popc(nb&xn)) over the packed sign plane.
+ * `layer` must be packed from alpha_i*sign(W) (all salient values exactly zero).  x: device [M][ldx] of
+ * x_dtype (any pbl_dtype, independent of the layer's); y: device float [M][ldy]; workspace: device,
+ * 16 B aligned, >= pbl_bireal_workspace(layer, M) bytes (packed activation sign planes). */
+PBL_API size_t pbl_bireal_workspace(const pbl_layer* layer, int64_t M);
+PBL_API int pbl_bireal_forward(const pbl_layer* layer, const void* x, int64_t ldx, int x_dtype, float* y, int64_t ldy,
+                               int64_t M, void* workspace, void* stream);
 
 /* Which kernel pbl_linear_forward would launch for this (layer, M): 0 = CUDA-core bit-plane
  * kernel (fp32 I/O), 1 = tcgen05 bit-plane GEMM (M above PBL_SKINNY_MAX_M, default 16),

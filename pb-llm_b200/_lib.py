@@ -20,7 +20,7 @@ class PblSizes(C.Structure):
 class PblLayerDesc(C.Structure):
     _fields_ = [("N", C.c_int64), ("K", C.c_int64), ("groupsize", C.c_int64), ("dtype", C.c_int32),
                 ("reserved", C.c_int32), ("planes", C.c_void_p), ("vptr", C.c_void_p), ("vals", C.c_void_p),
-                ("affine", C.c_void_p), ("bias", C.c_void_p)]
+                ("affine", C.c_void_p), ("bias", C.c_void_p), ("sign_planes", C.c_void_p)]
 
 
 # name -> (restype, argtypes): every symbol include/pbllm.h declares
@@ -39,6 +39,9 @@ SYMBOLS = {
                                      C.c_void_p]),
     "pbl_forward_host_workspace": (C.c_size_t, [C.c_void_p, C.c_int64]),
     "pbl_linear_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "pbl_bireal_workspace": (C.c_size_t, [C.c_void_p, C.c_int64]),
+    "pbl_bireal_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                     C.c_void_p]),
     "pbl_select_kernel": (C.c_int, [C.c_void_p, C.c_int64]),
     "pbl_launch_count": (C.c_int64, []),
     "pbl_last_error": (C.c_char_p, []),
@@ -73,7 +76,7 @@ def load():
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.pbl_abi_version() != 1:
+    if lib.pbl_abi_version() != 2:
         raise RuntimeError("libpbllm.so ABI version mismatch")
     _lib = lib
     return lib

@@ -151,6 +151,7 @@ int pbl_layer_create(const pbl_layer_desc* d, pbl_layer** out) {
     L->tiles_per_group = (sz.groups == 1) ? (int)sz.tiles_c : (int)(L->groupsize / kTileCols);
     L->planes = (const uint4*)d->planes; L->vptr = (const uint32_t*)d->vptr; L->vals = d->vals;
     L->affine = (const float2*)d->affine; L->bias = (const float*)d->bias;
+    L->sign_planes = (const uint2*)d->sign_planes;
     *out = reinterpret_cast<pbl_layer*>(L);
     return PBL_OK;
 }
@@ -216,6 +217,26 @@ int pbl_linear_forward(const pbl_layer* layer, const void* x, int64_t ldx, void*
     if (k == 1) return launch_gemm_tc(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
     if (k == 2) return launch_skinny(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
     return launch_gemv(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
+}
+
+size_t pbl_bireal_workspace(const pbl_layer* layer, int64_t M) {
+    if (!layer || M <= 0) return 0;
+    return bireal_workspace_bytes(*reinterpret_cast<const Layer*>(layer), M);
+}
+
+int pbl_bireal_forward(const pbl_layer* layer, const void* x, int64_t ldx, int x_dtype, float* y, int64_t ldy, int64_t M,
+                       void* workspace, void* stream) {
+    if (!layer) { set_error("pbl_bireal_forward: null layer"); return PBL_ERR_NULL; }
+    const Layer& L = *reinterpret_cast<const Layer*>(layer);
+    if (M < 0 || M > 65535LL * 8) { set_error("pbl_bireal_forward: bad M=%lld", (long long)M); return PBL_ERR_SHAPE; }
+    if (M == 0) return PBL_OK;
+    if (!x || !y || !workspace) { set_error("pbl_bireal_forward: null pointer"); return PBL_ERR_NULL; }
+    if (!valid_dtype(x_dtype)) { set_error("pbl_bireal_forward: bad x dtype %d", x_dtype); return PBL_ERR_DTYPE; }
+    if (ldx < L.K || ldy < L.N) { set_error("pbl_bireal_forward: leading dimension too small"); return PBL_ERR_SHAPE; }
+    if (!aligned16(workspace)) { set_error("pbl_bireal_forward: workspace must be 16 B aligned"); return PBL_ERR_ALIGN; }
+    int rc = device_check_impl();
+    if (rc) return rc;
+    return launch_bireal(L, x, ldx, x_dtype, y, ldy, M, workspace, (cudaStream_t)stream);
 }
 
 size_t pbl_forward_host_workspace(const pbl_layer* layer, int64_t M) {

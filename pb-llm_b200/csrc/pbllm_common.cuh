@@ -25,6 +25,7 @@ struct Layer {  // the opaque pbl_layer
     const void* vals;
     const float2* affine; // [n_pad][groups] {lo, hi}
     const float* bias;
+    const uint2* sign_planes;  // optional compact sign-only planes (nnz == 0 layers)
 };
 
 void set_error(const char* fmt, ...);
@@ -65,5 +66,8 @@ int launch_gemm_tc(const Layer& L, const void* x, int64_t ldx, void* y, int64_t 
 bool gemm_tc_supported(const Layer& L, const void* x, int64_t ldx, const void* y, int64_t ldy, int64_t M);
 int launch_skinny(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s);
 bool skinny_supported(const Layer& L, int64_t M);
+size_t bireal_workspace_bytes(const Layer& L, int64_t M);
+int launch_bireal(const Layer& L, const void* x, int64_t ldx, int x_dtype, float* y, int64_t ldy, int64_t M, void* workspace,
+                  cudaStream_t s);
 
 }  // namespace pbl

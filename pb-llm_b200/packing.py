@@ -98,9 +98,13 @@ class PackedLinear:
         return self
 
     def _create(self):
+        self.sign_planes = None
+        if self.nnz == 0:   # pure binary layer: keep a compact copy of the sign words for the XNOR-popcount path
+            self.sign_planes = self.planes.view(-1, 4)[:, :2].contiguous()
         d = _lib.PblLayerDesc(self.N, self.K, self.groupsize, _DT[self.dtype], 0, self.planes.data_ptr(),
                               self.vptr.data_ptr(), self.vals.data_ptr(), self.affine.data_ptr(),
-                              0 if self.bias is None else self.bias.data_ptr())
+                              0 if self.bias is None else self.bias.data_ptr(),
+                              0 if self.sign_planes is None else self.sign_planes.data_ptr())
         h = C.c_void_p()
         _lib.check(_lib.load().pbl_layer_create(C.byref(d), C.byref(h)), "pbl_layer_create")
         self.handle = h
@@ -149,6 +153,36 @@ class PackedLinear:
         if out is not None:
             return y
         return y if x.dim() == 2 else y.view(*x.shape[:-1], self.N)
+
+    def bireal_forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None,
+                       workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """XNOR-popcount forward (pbl_bireal_forward): y = sign(x) @ w_sim.T in fp32, no bias. The layer
+        must have been packed from alpha*sign(W) (its salient values are all exactly zero)."""
+        if not x.is_cuda:
+            raise RuntimeError("pb-llm_b200 forward needs CUDA activations (no CPU fallback)")
+        if x.dtype not in _DT:
+            raise RuntimeError(f"unsupported activation dtype {x.dtype}")
+        if x.shape[-1] != self.K:
+            raise RuntimeError(f"last dim of x is {x.shape[-1]}, expected in_features={self.K}")
+        x2 = x if x.dim() == 2 else x.reshape(-1, self.K)
+        if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < self.K):
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        y = out if out is not None else torch.empty((M, self.N), dtype=torch.float32, device=x.device)
+        if M:
+            lib = _lib.load()
+            with torch.cuda.device(x.device):
+                ws = workspace if workspace is not None else \
+                    torch.empty(int(lib.pbl_bireal_workspace(self.handle, M)), dtype=torch.uint8, device=x.device)
+                rc = lib.pbl_bireal_forward(self.handle, x2.data_ptr(), x2.stride(0) if M > 1 else self.K, _DT[x.dtype],
+                                            y.data_ptr(), y.stride(0), M, ws.data_ptr(), _stream(x.device))
+            _lib.check(rc, "pbl_bireal_forward")
+        if out is not None:
+            return y
+        return y if x.dim() == 2 else y.view(*x.shape[:-1], self.N)
+
+    def bireal_workspace_bytes(self, M: int) -> int:
+        return int(_lib.load().pbl_bireal_workspace(self.handle, M))
 
     def forward_host(self, x_host: torch.Tensor, y_host: torch.Tensor, workspace: torch.Tensor):
         """End-to-end form with HOST buffers (pbl_linear_forward_host): H2D, kernel, D2H, sync."""

@@ -137,6 +137,39 @@ class IrBinaryLinear(XnorBinaryLinear):
     forward is torch.sign, :31-38)."""
 
 
+class BiRealLinear(_PackedBase):
+    """Reference quantizer.py:131-169 -- the reference's only true XNOR-popcount layer: activations
+    are binarized as well (`sign(x)`, :153; the polynomial STE terms :154-165 cancel in the forward
+    value), weights are `mean_row|W| * sign(W)` (:138-148, no mean subtraction), and the bias is
+    DROPPED (`F.linear(input, w)`, :168). Output is fp32 like the reference's (its masks promote to
+    float32). Forward runs pbl_bireal_forward: popcounts over the packed sign plane."""
+
+    def __init__(self, weight, bias) -> None:
+        super().__init__()
+        self._init_params(weight, bias, cast_fp32=True)
+
+    def quant_weight(self):
+        real_weights = self.weight.data
+        scaling_factor = torch.mean(abs(real_weights), dim=1, keepdim=True)      # :139
+        return scaling_factor * torch.sign(real_weights)                         # :141 (forward value of :143-147)
+
+    def _effective_weight(self):
+        return self.quant_weight(), None, -1
+
+    @torch.no_grad()
+    def pack(self, keep_latent: bool = True, verify: bool = False):
+        p = super().pack(keep_latent, verify)
+        if p.nnz and bool((p.vals[: p.nnz] != 0).any()):
+            raise RuntimeError("BiRealLinear: packed layer has non-zero salient values; XNOR-popcount path needs sign weights")
+        return p
+
+    def forward(self, input):
+        return self.packed().bireal_forward(input)
+
+    def to_regular_linear(self):
+        raise NotImplementedError("BiRealLinear binarizes its activations; it has no dense nn.Linear equivalent")
+
+
 class PackedFakeQuantLinear(_PackedBase):
     """A plain nn.Linear holding GPTQ-PB fake-quant weights (what gptq_pb/gptq.py:180-184 writes
     and the reference then evaluates as a dense fp16 GEMM), served from the packed form.
