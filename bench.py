@@ -348,12 +348,29 @@ def main():
             with torch.cuda.graph(graph, stream=side):
                 dstep()
         ms_d, _ = timed(graph.replay, 50, 5)
+        # batch-1 decode (the classic GEMV regime) for reference
+        x1_in = {k: v[:1].contiguous() for k, v in xin.items()}
+        d1outs = [torch.empty(1, p.N, device=dev, dtype=torch.float16) for p in layers[0]]
+
+        def d1step():
+            for row in layers:
+                for i, p in enumerate(row):
+                    p.forward(x1_in[SHAPES[i][3]], out=d1outs[i])
+
+        graph1 = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            d1step()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph1, stream=side):
+                d1step()
+        ms_d1, _ = timed(graph1.replay, 50, 5)
         G = 1
         b_bin = nk / 8 + 4 * sum(p.N for row in layers for p in row) * G + 2 * Md * sum(p.K + p.N for row in layers for p in row)
         b_sal = 2 * nnz + sum(p.N + 1 for row in layers for p in row)
         ach = (b_bin + b_sal) / (ms_d * 1e-3) / 1e9
         decode = {"tokens_per_s": Md * (1 if rowshard else world) / (ms_d * 1e-3), "ms_per_step": ms_d,
-                  "ms_per_step_eager_python_launch": ms_d_eager, "batch": Md, "launch": "CUDA graph replay of the 224 launches",
+                  "ms_per_step_eager_python_launch": ms_d_eager, "batch": Md, "ms_per_step_batch1": ms_d1,
+                  "batch1_actual_bytes_gbs": packed_bytes / (ms_d1 * 1e-3) / 1e9, "launch": "CUDA graph replay of the 224 launches",
                   "kernel": "pbl mma.sync bit-plane skinny kernel" if layers[0][0].select_kernel(Md) == 2 else "pbl CUDA-core bit-plane kernel",
                   "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                                "traffic": None, "algorithmic_bytes_per_step": b_bin + b_sal,

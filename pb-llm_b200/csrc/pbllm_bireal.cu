@@ -13,7 +13,7 @@
 
 namespace pbl {
 
-constexpr int kBrWarps = 8;
+constexpr int kBrWarps = 16;
 
 // x [M][ldx] (any dtype) -> xb [M][tiles_c] uint4 {xp[0:32], xp[32:64], xn[0:32], xn[32:64]}, dx [M][tiles_c] int
 template <typename T>
@@ -52,7 +52,23 @@ bireal_xnor_kernel(const uint4* __restrict__ planes, const uint2* __restrict__ s
     int cur_g = -1;
     float2 a = make_float2(0.f, 0.f);
 
+    auto load_planes = [&](int kb) {
+        uint4 p = make_uint4(0u, 0u, 0u, 0u);
+        if (kb < tiles_c) {
+            if constexpr (kCompact) {   // sign words only (pure binary layer): half the HBM bytes
+                const uint2 sp = __ldg(sign_planes + (tr * tiles_c + kb) * kTileRows + rgi * kRgRows + lane);
+                p = make_uint4(sp.x, sp.y, 0u, 0u);
+            } else {
+                p = __ldg(planes + (tr * tiles_c + kb) * kTileRows + rgi * kRgRows + lane);
+            }
+        }
+        return p;
+    };
+    uint4 pn0 = load_planes(wid), pn1 = load_planes(wid + kBrWarps);   // two k-blocks in flight per warp
     for (int kb = wid; kb < tiles_c; kb += kBrWarps) {
+        const uint4 p = pn0;
+        pn0 = pn1;
+        pn1 = load_planes(kb + 2 * kBrWarps);
         const int g = kb / tiles_per_group;
         if (g != cur_g) {   // fold the finished group, fetch the next {lo,hi}
 #pragma unroll
@@ -60,15 +76,8 @@ bireal_xnor_kernel(const uint4* __restrict__ planes, const uint2* __restrict__ s
             a = __ldg(affine + row * groups + g);
             cur_g = g;
         }
-        uint4 p;
         bool any_sal = false;
-        if constexpr (kCompact) {   // sign words only (pure binary layer): half the HBM bytes
-            const uint2 sp = __ldg(sign_planes + (tr * tiles_c + kb) * kTileRows + rgi * kRgRows + lane);
-            p = make_uint4(sp.x, sp.y, 0u, 0u);
-        } else {
-            p = __ldg(planes + (tr * tiles_c + kb) * kTileRows + rgi * kRgRows + lane);
-            any_sal = __any_sync(0xffffffffu, (p.z | p.w) != 0u);
-        }
+        if constexpr (!kCompact) any_sal = __any_sync(0xffffffffu, (p.z | p.w) != 0u);
         const uint32_t nb0 = ~(p.x | p.z), nb1 = ~(p.y | p.w);
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
