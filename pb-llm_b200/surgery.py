@@ -120,3 +120,67 @@ def load_bnn(model, load_path):
             q.to(module.weight.device)
             setattr(father, leaf, q)
     return model
+
+
+# ---- packed on-disk format: what save_bnn / save_pretrained only account for ----------------
+_PACKED_VERSION = 1
+
+
+@torch.no_grad()
+def save_packed(model: nn.Module, save_path: str):
+    """Write every packed module's buffers (planes / vptr / vals / affine / bias) instead of 16-bit
+    latent or fake-quant weights: the checkpoint is as small as the model is in HBM (~3.6 bit/weight at
+    low_frac 0.9) where the reference's save_bnn (utils.py:87-94) and save_pretrained
+    (gptq_pb/run.py:315-319) store 16 bit/weight. meta.json keeps the reference's name -> class map."""
+    os.makedirs(save_path, exist_ok=True)
+    meta, tensors = {"version": _PACKED_VERSION, "layers": {}}, {}
+    for name, m in model.named_modules():
+        if isinstance(m, BinaryInterface) and hasattr(m, "packed"):
+            p = m.packed()
+            meta["layers"][name] = {"cls": m.__class__.__name__, "N": p.N, "K": p.K, "groupsize": p.groupsize,
+                                    "dtype": str(p.dtype).replace("torch.", ""), "nnz": p.nnz,
+                                    "bias": p.bias is not None}
+            for k, v in p.buffers().items():
+                if v is not None:
+                    tensors[f"{name}::{k}"] = (v[: p.nnz + 8] if k == "vals" else v).cpu()
+    with open(os.path.join(save_path, "packed_meta.json"), "w") as f:
+        json.dump(meta, f)
+    torch.save(tensors, os.path.join(save_path, "packed_weights.pth"))
+    return meta
+
+
+@torch.no_grad()
+def load_packed(model: nn.Module, load_path: str, device=None):
+    """Install packed modules from a save_packed() checkpoint into a freshly constructed model (its
+    nn.Linear layers are replaced by name, like utils.load_bnn does, utils.py:102-122). No latent
+    weights are materialised: the modules serve straight from the loaded buffers."""
+    from .packing import PackedLinear
+    with open(os.path.join(load_path, "packed_meta.json")) as f:
+        meta = json.load(f)
+    if meta.get("version") != _PACKED_VERSION:
+        raise RuntimeError("unknown packed checkpoint version")
+    tensors = torch.load(os.path.join(load_path, "packed_weights.pth"))
+    names = {name: m for name, m in model.named_modules()}
+    for name, info in meta["layers"].items():
+        old = names[name]
+        dev = device if device is not None else next(old.parameters()).device
+        dt = getattr(torch, info["dtype"])
+        get = lambda k: tensors[f"{name}::{k}"].to(dev)  # noqa: E731
+        p = PackedLinear.from_buffers(info["N"], info["K"], info["groupsize"], dt, get("planes"), get("vptr"), get("vals"),
+                                      get("affine"), get("bias") if info["bias"] else None)
+        cls = getattr(_quant, info["cls"])
+        q = cls.__new__(cls)
+        nn.Module.__init__(q)
+        q.weight = nn.Parameter(torch.empty(0, dtype=dt, device=dev), requires_grad=False)
+        q.bias = None if not info["bias"] else nn.Parameter(p.bias.to(dt), requires_grad=False)
+        q._packed, q._packed_key, q._latent_dropped = p, None, True
+        q.global_name, q.out_features, q.in_features = name, info["N"], info["K"]
+        for attr, val in (("outlier_mask", None), ("binary_scale", None), ("outlier_nbits", None), ("low_mask", None),
+                          ("outlier_fraction", None), ("outlier_scale", 1), ("train_outlier", False), ("printed", False),
+                          ("groupsize", info["groupsize"])):
+            if not hasattr(q, attr):
+                setattr(q, attr, val)
+        ind = name.rfind(".")
+        father = names[""] if ind == -1 else names[name[:ind]]
+        setattr(father, name[ind + 1:], q)
+    return model

@@ -66,3 +66,25 @@ def test_hf_model_drop_in(make, method):
     with torch.no_grad():
         again = model(ids).logits
     assert torch.equal(again, logits)
+
+
+def test_packed_checkpoint_roundtrip(tmp_path):
+    """save_packed / load_packed: the on-disk model is the packed model."""
+    torch.manual_seed(1)
+    model = tiny_llama().to(DEV).half().eval()
+    pb.replace_with_qlinear(model, "xnor_outlier", 0.1, model_id="tiny/")
+    ids = torch.randint(0, 512, (2, 16), device=DEV)
+    with torch.no_grad():
+        ref = model(ids).logits
+    meta = pb.save_packed(model, str(tmp_path / "packed"))
+    assert len(meta["layers"]) == 15
+    import os
+    dense_bytes = sum(i["N"] * i["K"] * 2 for i in meta["layers"].values())
+    assert os.path.getsize(tmp_path / "packed" / "packed_weights.pth") < 0.45 * dense_bytes
+    torch.manual_seed(1)
+    fresh = tiny_llama().to(DEV).half().eval()                     # same non-linear parameters (embeddings, norms)
+    pb.load_packed(fresh, str(tmp_path / "packed"))
+    assert all(m.weight.numel() == 0 for m in fresh.modules() if isinstance(m, pb.BinaryInterface))
+    with torch.no_grad():
+        out = fresh(ids).logits
+    assert torch.equal(out, ref)
