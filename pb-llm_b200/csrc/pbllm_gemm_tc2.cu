@@ -146,10 +146,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) 
             uint32_t ph = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int t = cluster_id + ti * num_clusters;
-                const int m0 = (t / p.n_tiles) * (2 * BMC) + (int)crank * BMC;
+                const int m0 = (t / p.n_tiles) * p.bm + (int)crank * (p.bm >> 1);
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(empty(s), ph ^ 1u);
-                    if (leader) mbar_arrive_expect_tx(full_a(s), 2u * kAStage);
+                    if (leader) mbar_arrive_expect_tx(full_a(s), (uint32_t)p.bm * 128u);   // both CTAs' boxes
                     tma_load_2d_2sm(smem_base + kOffA + s * kAStage, &tmap_x, kb * BK, m0, full_a(s) & 0xFEFFFFFFu);
                     if (++s == kStages) { s = 0; ph ^= 1u; }
                 }
@@ -164,8 +164,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) 
             uint32_t ph = 0, acc_ph = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int t = cluster_id + ti * num_clusters;
-                const int m0 = (t / p.n_tiles) * (2 * BMC);
-                const int halves = (m0 + 128 < p.M) ? 2 : 1;
+                const int m0 = (t / p.n_tiles) * p.bm;
+                const int halves = (p.bm == 2 * BMC && m0 + 128 < p.M) ? 2 : 1;
                 mbar_wait_cluster(tmem_empty, acc_ph ^ 1u);
                 tc_fence_after();
                 for (int kb = 0; kb < KB; ++kb) {
@@ -340,9 +340,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) 
         const uint32_t tmem_empty_leader = mapa_rank0(tmem_empty);
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int t = cluster_id + ti * num_clusters;
-            const int mp = (t / p.n_tiles) * (2 * BMC);
-            const int m0 = mp + (int)crank * BMC, n0 = (t % p.n_tiles) * BN;
-            const int halves = (mp + 128 < p.M) ? 2 : 1;      // which accumulators the MMA warp actually wrote
+            const int mp = (t / p.n_tiles) * p.bm;
+            const int m0 = mp + (int)crank * (p.bm >> 1), n0 = (t % p.n_tiles) * BN;
+            const int halves = (p.bm == 2 * BMC && mp + 128 < p.M) ? 2 : 1;      // which accumulators the MMA warp wrote
             mbar_wait(tmem_full, acc_ph);
             tc_fence_after();
             for (int h = 0; h < halves; ++h) {
@@ -401,7 +401,7 @@ bool gemm_tc2_enabled(const Layer& L, int64_t M) {
     (void)L;
     if (mode == 0) return false;
     if (mode == 2) return true;
-    return M >= 2048;
+    return M > 256;
 }
 
 int launch_gemm_tc2(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s) {
@@ -413,10 +413,14 @@ int launch_gemm_tc2(const Layer& L, const void* x, int64_t ldx, void* y, int64_t
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
+    // pair tile = 512 tokens (each CTA two UMMA halves) when that fills the GPU, else 256 tokens (one half per
+    // CTA): twice the tiles, and the per-CTA weight expansion still amortised over a 256-token pair MMA.
+    const int n_tiles = (int)((L.N + tc2::BN - 1) / tc2::BN);
+    const int bm = (((M + 511) / 512) * (int64_t)n_tiles >= num_sms / 2) ? 512 : 256;
     CUtensorMap tmap;
     const cuuint64_t gdim[2] = {(cuuint64_t)L.K, (cuuint64_t)M};
     const cuuint64_t gstr[1] = {(cuuint64_t)ldx * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)tc2::BK, (cuuint32_t)tc2::BMC};
+    const cuuint32_t box[2] = {(cuuint32_t)tc2::BK, (cuuint32_t)(bm / 2)};
     const cuuint32_t estr[2] = {1, 1};
     CUresult cr = enc(&tmap, L.dtype == PBL_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                       const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -427,9 +431,9 @@ int launch_gemm_tc2(const Layer& L, const void* x, int64_t ldx, void* y, int64_t
     p.planes = L.planes; p.vptr = L.vptr; p.vals = reinterpret_cast<const uint16_t*>(L.vals); p.affine = L.affine;
     p.bias = L.bias; p.y = y; p.ldy = ldy; p.M = (int)M; p.N = (int)L.N; p.K = (int)L.K;
     p.tiles_r = (int)L.tiles_r; p.tiles_c = (int)L.tiles_c; p.groups = (int)L.groups; p.tiles_per_group = L.tiles_per_group;
-    p.bm = 2 * tc2::BMC;
+    p.bm = bm;
     p.m_tiles = (int)((M + p.bm - 1) / p.bm);
-    p.n_tiles = (int)((L.N + tc2::BN - 1) / tc2::BN);
+    p.n_tiles = n_tiles;
     p.kblocks = (int)L.tiles_c;
 
     static bool attr_set[2] = {false, false};
