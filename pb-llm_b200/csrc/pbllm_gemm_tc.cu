@@ -397,14 +397,20 @@ int launch_gemm_tc(const Layer& L, const void* x, int64_t ldx, void* y, int64_t 
     p.n_tiles = n_tiles;
     p.kblocks = (int)L.tiles_c;
 
-    static bool attr_set[2] = {false, false};
+    static bool attr_set_dev[2][64] = {};   // function attributes are per device
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    bool* attr_set = nullptr;
+    bool attr_local[2] = {false, false};
+    attr_set = (cur_dev >= 0 && cur_dev < 64) ? nullptr : attr_local;
     const int which = L.dtype == PBL_F16 ? 0 : 1;
     auto kern = which == 0 ? gemm_tc_kernel<__half> : gemm_tc_kernel<__nv_bfloat16>;
-    if (!attr_set[which]) {
+    bool& attr_done = attr_set ? attr_set[which] : attr_set_dev[which][cur_dev];
+    if (!attr_done) {
         int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes),
                             "cudaFuncSetAttribute(smem)");
         if (rc) return rc;
-        attr_set[which] = true;
+        attr_done = true;
     }
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < num_sms ? tiles : num_sms;

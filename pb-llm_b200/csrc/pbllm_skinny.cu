@@ -297,15 +297,21 @@ bool skinny_supported(const Layer& L, int64_t M) {
 int launch_skinny(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s) {
     const dim3 grid((unsigned)(L.n_pad / kRgRows), (unsigned)((M + sk::kTok - 1) / sk::kTok));
     const int smem = sk::kWarps * sk::kWarpBytes;
-    static bool attr_set[2] = {false, false};
+    static bool attr_set_dev[2][64] = {};   // function attributes are per device
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    bool* attr_set = nullptr;
+    bool attr_local[2] = {false, false};
+    attr_set = (cur_dev >= 0 && cur_dev < 64) ? nullptr : attr_local;
     const int which = L.dtype == PBL_F16 ? 0 : 1;
-    if (!attr_set[which]) {
+    bool& attr_done = attr_set ? attr_set[which] : attr_set_dev[which][cur_dev];
+    if (!attr_done) {
         cudaError_t e = which == 0
             ? cudaFuncSetAttribute(skinny_mma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
             : cudaFuncSetAttribute(skinny_mma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         int rc = check_cuda(e, "cudaFuncSetAttribute(skinny smem)");
         if (rc) return rc;
-        attr_set[which] = true;
+        attr_done = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
