@@ -451,3 +451,25 @@ def test_full_size_properties_llama7b_shapes(N, K, M):
     ref = x1.double() @ w.double().t()                              # dense fp64 check of the same w_sim
     assert ((y1.double() - ref).abs().max() / ref.abs().max()) <= 1e-3
     assert torch.equal(p.forward(x1), p.forward(x1))                # deterministic (no atomics)
+
+
+# ---- BASELINE configs[1]: OPT-1.3b shapes through the drop-in constructor (magnitude mask, f = 0.1) --------------
+@pytest.mark.parametrize("N,K", [(2048, 2048), (8192, 2048), (2048, 8192)])
+def test_full_size_outlier_module_opt13b_shapes(N, K):
+    gen = torch.Generator(device=DEV).manual_seed(N * 3 + K)
+    W = (torch.empty(N, K, device=DEV).normal_(0, 0.02, generator=gen)
+         * (1 + 4 * (torch.rand(N, K, device=DEV, generator=gen) < 0.02))).half()      # heavy-tailed
+    b = (torch.randn(N, device=DEV, generator=gen) * 0.1).half()
+    m = pb.BinaryXnorExceptOutliersLinear(W.clone(), b, 0.1).eval()
+    x = torch.randn(1, 2048, K, device=DEV, generator=gen).half()                       # seq_len 2048, batch 1
+    y = m(x)
+    assert m.packed().select_kernel(2048) == 1
+    frac = float(m.outlier_mask.float().mean())
+    assert abs(frac - 0.1) < 2e-3 and tuple(m.binary_scale.shape) == (1, 1)
+    w_sim = m.dense_weight()
+    assert torch.equal(w_sim, m.binarize_except_outliers())                             # packed form == reference tensor
+    ref = x.double().view(-1, K) @ w_sim.double().t() + b.double()
+    assert float((y.double().view(-1, N) - ref).abs().max() / ref.abs().max()) <= 1e-3
+    y1 = m(x[:, :1])                                                                    # decode-sized call, skinny kernel
+    assert float((y1.double().view(-1, N) - ref[:1]).abs().max() / ref[:1].abs().max()) <= 1e-3
+    assert 1.0 < m.outlier_nbits < 2.0 and m.packed().bits_per_weight() < 4.0
