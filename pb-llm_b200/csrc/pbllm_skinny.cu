@@ -19,13 +19,12 @@
 namespace pbl {
 
 namespace sk {
-constexpr int kWarps = 16;
 constexpr int kTok = 8;                         // tokens per pass (mma N)
 constexpr int kXrStride = kTileCols + 8;        // halves per token row (+8: conflict-free B-fragment LDS)
 constexpr int kXrBytes = kTok * kXrStride * 2;  // 1152
 constexpr int kTileBytes = kRgRows * kTileCols * 2;  // 4096: the warp's 32x64 16-bit weight tile (swizzled)
 constexpr int kScrBytes = 1024;                 // staged salient values (512 x 16 bit)
-constexpr int kWarpBytes = kTileBytes + kXrBytes + kScrBytes;  // 6272
+constexpr int kWarpBytes = kTileBytes + kXrBytes + kScrBytes;  // 6272 per warp
 static_assert(kWarpBytes % 128 == 0, "alignment");
 }  // namespace sk
 
@@ -69,8 +68,8 @@ template <typename T> __device__ __forceinline__ float sk_val(uint16_t v);
 template <> __device__ __forceinline__ float sk_val<__half>(uint16_t v) { return __half2float(__ushort_as_half(v)); }
 template <> __device__ __forceinline__ float sk_val<__nv_bfloat16>(uint16_t v) { return __uint_as_float((uint32_t)v << 16); }
 
-template <typename T>
-__global__ void __launch_bounds__(sk::kWarps * 32)
+template <typename T, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32)
 skinny_mma_kernel(const uint4* __restrict__ planes, const uint32_t* __restrict__ vptr, const uint16_t* __restrict__ vals,
                   const float2* __restrict__ affine, const float* __restrict__ bias, const T* __restrict__ x, int64_t ldx,
                   T* __restrict__ y, int64_t ldy, int M, int N, int K, int tiles_c, int groups, int tiles_per_group) {
@@ -95,18 +94,23 @@ skinny_mma_kernel(const uint4* __restrict__ planes, const uint32_t* __restrict__
 #pragma unroll
     for (int i = 0; i < 4; ++i) cacc[0][i] = cacc[1][i] = 0.f;
 
-    // ---- prefetch helpers -----------------------------------------------------------------------
+    // ---- prefetch helpers: pointers advance by kWarps k-blocks per iteration (no per-iteration index math) ----
     struct Meta { uint4 pw; uint32_t cs, ce; };
-    auto load_meta = [&](int kb) {
+    const uint4* pl_ptr = planes + ((int64_t)tr * tiles_c + wid) * kTileRows + rgi * kRgRows + lane;
+    const uint32_t* vp_ptr = vptr + ((int64_t)tr * tiles_c + wid) * kRgPerTile + rgi;
+    int kb_meta = wid;                                   // k-block the meta pointers refer to
+    auto load_meta = [&]() {
         Meta mt;
         mt.pw = make_uint4(0, 0, 0, 0);
         mt.cs = mt.ce = 0;
-        if (kb < tiles_c) {
-            const int64_t tile = (int64_t)tr * tiles_c + kb;
-            mt.pw = __ldg(planes + tile * kTileRows + rgi * kRgRows + lane);
-            mt.cs = __ldg(vptr + tile * kRgPerTile + rgi);
-            mt.ce = __ldg(vptr + tile * kRgPerTile + rgi + 1);
+        if (kb_meta < tiles_c) {
+            mt.pw = __ldg(pl_ptr);
+            mt.cs = __ldg(vp_ptr);
+            mt.ce = __ldg(vp_ptr + 1);
         }
+        pl_ptr += kWarps * kTileRows;
+        vp_ptr += kWarps * kRgPerTile;
+        kb_meta += kWarps;
         return mt;
     };
     auto load_vals = [&](const Meta& mt, uint4& q0, uint4& q1) {
@@ -116,20 +120,36 @@ skinny_mma_kernel(const uint4* __restrict__ planes, const uint32_t* __restrict__
         if (o0 < b1) q0 = __ldg(reinterpret_cast<const uint4*>(base + o0));
         if (o1 < b1) q1 = __ldg(reinterpret_cast<const uint4*>(base + o1));
     };
-    const bool x_al32 = ((ldx & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 3u) == 0);
-    auto load_x = [&](int kb, uint32_t (&xv)[kTok]) {   // lane holds columns 2*lane, 2*lane+1 of every token
-        const int col = kb * kTileCols + 2 * lane;
-#pragma unroll
-        for (int m = 0; m < kTok; ++m) {
-            uint32_t v = 0;
-            if (kb < tiles_c && m0 + m < M) {
-                const uint16_t* p = x16 + (int64_t)(m0 + m) * ldx + col;
-                if (col + 1 < K) {
-                    if (x_al32) v = __ldg(reinterpret_cast<const uint32_t*>(p));
-                    else v = (uint32_t)p[0] | ((uint32_t)p[1] << 16);
-                } else if (col < K) v = (uint32_t)p[0];
+    // activations: lane -> (token = lane>>2, 16-column segment = lane&3) of the 8 x 64 tile: two 16 B loads.
+    // Fast path needs 16 B-aligned rows and whole 16-column segments; anything else takes the generic path.
+    const int xtok = lane >> 2, xseg = lane & 3;
+    const bool x_fast = ((ldx & 7) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((K & 15) == 0);
+    const bool x_tok_ok = (m0 + xtok) < M;
+    const uint16_t* x_lane = x16 + (int64_t)(m0 + (x_tok_ok ? xtok : 0)) * ldx + 16 * xseg;
+    auto load_x = [&](int kb, uint4& xa, uint4& xb2) {
+        xa = make_uint4(0, 0, 0, 0);
+        xb2 = make_uint4(0, 0, 0, 0);
+        if (kb >= tiles_c) return;
+        const int col = kb * kTileCols + 16 * xseg;
+        if (x_fast) {
+            if (x_tok_ok && col < K) {
+                const uint4* p4 = reinterpret_cast<const uint4*>(x_lane + (int64_t)kb * kTileCols);
+                xa = __ldg(p4);
+                xb2 = __ldg(p4 + 1);
             }
-            xv[m] = v;
+        } else if (x_tok_ok) {                            // generic: element loads with bounds checks
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = col + 2 * i;
+                const uint16_t* p = x_lane + (int64_t)kb * kTileCols + 2 * i;
+                uint32_t v = 0;
+                if (c < K) v = (uint32_t)p[0];
+                if (c + 1 < K) v |= (uint32_t)p[1] << 16;
+                w[i] = v;
+            }
+            xa = make_uint4(w[0], w[1], w[2], w[3]);
+            xb2 = make_uint4(w[4], w[5], w[6], w[7]);
         }
     };
 
@@ -137,11 +157,11 @@ skinny_mma_kernel(const uint4* __restrict__ planes, const uint32_t* __restrict__
     // everything below up to griddepcontrol.wait touches only immutable packed weights.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    int cur_g = wid < tiles_c ? wid / tiles_per_group : 0;
+    const bool grouped = groups > 1;
+    int cur_g = (grouped && wid < tiles_c) ? wid / tiles_per_group : 0;
     float2 a_first = __ldg(affine + (int64_t)row * groups + cur_g);      // overlaps the meta / value loads
-    Meta mt0 = load_meta(wid), mt1 = load_meta(wid + kWarps);
+    Meta mt0 = load_meta(), mt1 = load_meta();
     uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
-    uint32_t xv[kTok];
     load_vals(mt0, q0, q1);
     uint32_t LL, DD;
     {
@@ -151,41 +171,48 @@ skinny_mma_kernel(const uint4* __restrict__ planes, const uint32_t* __restrict__
     }
     // activations (and y) belong to the producer kernel: wait for it before the first read of x
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    load_x(wid, xv);
+    uint4 xn0, xn1;
+    load_x(wid, xn0, xn1);
 
-    // ldmatrix source rows for this lane: matrix i = lane>>3 -> (row block i&1, k chunk i>>1)
-    const int lm_row = (lane & 7) + ((lane >> 3) & 1) * 8;      // row within a 16-row tile
-    const uint32_t lm_kc = (uint32_t)(lane >> 4);                // 0/1: which 8-column chunk of the k16 step
+    // ldmatrix source address for this lane: matrix i = lane>>3 -> (row block i&1, k chunk i>>1); the k16 step q
+    // only flips address bits 5-6 (chunk = (kc ^ r7) ^ 2q), so addr(q) = base ^ (q << 5).
+    const uint32_t lm_row = (uint32_t)((lane & 7) + ((lane >> 3) & 1) * 8);
+    const uint32_t lm_kc = (uint32_t)(lane >> 4);
+    const uint32_t lm_base0 = tile_s + lm_row * 128u + (((lm_kc ^ (lm_row & 7u))) << 4);
+    const uint32_t lm_base1 = lm_base0 + 16u * 128u;
+    const uint32_t xr_s = (uint32_t)__cvta_generic_to_shared(xr);
+    const uint32_t xr_st = xr_s + (uint32_t)(xtok * kXrStride + 16 * xseg) * 2u;      // where my two 16 B x segments go
+    const uint32_t bfr_s = xr_s + (uint32_t)(g4 * kXrStride + 2 * t4) * 2u;           // my B-fragment words
 
     for (int kb = wid; kb < tiles_c; kb += kWarps) {
         const uint4 pw = mt0.pw;
         const uint32_t cs = mt0.cs, ce = mt0.ce;
         const uint4 v0 = q0, v1 = q1;
-        uint32_t xc[kTok];
-#pragma unroll
-        for (int m = 0; m < kTok; ++m) xc[m] = xv[m];
+        const uint4 xc0 = xn0, xc1 = xn1;
         // next items' global loads first
-        const Meta mt2 = load_meta(kb + 2 * kWarps);
+        const Meta mt2 = load_meta();
         load_vals(mt1, q0, q1);
-        load_x(kb + kWarps, xv);
+        load_x(kb + kWarps, xn0, xn1);
         mt0 = mt1;
         mt1 = mt2;
 
-        const int g = kb / tiles_per_group;
-        if (g != cur_g) {
-            cur_g = g;
-            const float2 a = __ldg(affine + (int64_t)row * groups + g);
-            const uint32_t lo = sk_bits16<T>(a.x), hi = sk_bits16<T>(a.y);
-            LL = lo | (lo << 16);
-            DD = (lo ^ hi) * 0x10001u;
+        if (grouped) {
+            const int g = kb / tiles_per_group;
+            if (g != cur_g) {
+                cur_g = g;
+                const float2 a = __ldg(affine + (int64_t)row * groups + g);
+                const uint32_t lo = sk_bits16<T>(a.x), hi = sk_bits16<T>(a.y);
+                LL = lo | (lo << 16);
+                DD = (lo ^ hi) * 0x10001u;
+            }
         }
 
         // ---- stage activations (row layout for the B fragments) and this row group's salient values
         __syncwarp();
         const uint32_t b0 = (cs * 2u) & ~15u;
         {
-#pragma unroll
-            for (int m = 0; m < kTok; ++m) *reinterpret_cast<uint32_t*>(xr + m * kXrStride + 2 * lane) = xc[m];
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xr_st), "r"(xc0.x), "r"(xc0.y), "r"(xc0.z), "r"(xc0.w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xr_st + 16u), "r"(xc1.x), "r"(xc1.y), "r"(xc1.z), "r"(xc1.w) : "memory");
             const uint32_t o0 = 16u * lane, o1 = o0 + 512u;
             if (b0 + o0 < ce * 2u) asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(scr + o0), "r"(v0.x), "r"(v0.y), "r"(v0.z), "r"(v0.w) : "memory");
             if (b0 + o1 < ce * 2u) asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(scr + o1), "r"(v1.x), "r"(v1.y), "r"(v1.z), "r"(v1.w) : "memory");
@@ -211,7 +238,7 @@ skinny_mma_kernel(const uint4* __restrict__ planes, const uint32_t* __restrict__
             }
         }
         // ... then patch the salient values over their positions
-        {
+        if (__any_sync(0xffffffffu, (pw.z | pw.w) != 0u)) {
             const uint32_t idx0 = (cs - (b0 >> 1)) + warp_excl_scan(__popc(pw.z) + __popc(pw.w), lane);
             if (ce - (b0 >> 1) <= 512u) {            // warp-uniform: the whole chunk is staged in shared memory
                 uint32_t sa = scr + idx0 * 2u;
@@ -251,12 +278,12 @@ skinny_mma_kernel(const uint4* __restrict__ planes, const uint32_t* __restrict__
         // ---- tensor cores: A fragments by ldmatrix from the swizzled tile, B fragments from xr ------------
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const uint32_t bq0 = *reinterpret_cast<const uint32_t*>(xr + g4 * kXrStride + 16 * q + 2 * t4);
-            const uint32_t bq1 = *reinterpret_cast<const uint32_t*>(xr + g4 * kXrStride + 16 * q + 2 * t4 + 8);
+            uint32_t bq0, bq1;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(bq0) : "r"(bfr_s + (uint32_t)(32 * q)) : "memory");
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(bq1) : "r"(bfr_s + (uint32_t)(32 * q + 16)) : "memory");
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const uint32_t rr = (uint32_t)(16 * h + lm_row);
-                const uint32_t addr = tile_s + rr * 128u + ((((uint32_t)(2 * q) + lm_kc) ^ (rr & 7u)) << 4);
+                const uint32_t addr = (h ? lm_base1 : lm_base0) ^ ((uint32_t)q << 5);
                 uint32_t a0, a1, a2, a3;
                 asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                              : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
@@ -294,28 +321,25 @@ bool skinny_supported(const Layer& L, int64_t M) {
     return (L.dtype == PBL_F16 || L.dtype == PBL_BF16) && M > 0 && M <= 65535LL * sk::kTok;
 }
 
-int launch_skinny(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s) {
+template <typename T, int kWarps>
+static int launch_skinny_t(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s, int which) {
     const dim3 grid((unsigned)(L.n_pad / kRgRows), (unsigned)((M + sk::kTok - 1) / sk::kTok));
-    const int smem = sk::kWarps * sk::kWarpBytes;
-    static bool attr_set_dev[2][64] = {};   // function attributes are per device
+    const int smem = kWarps * sk::kWarpBytes;
+    static bool attr_set_dev[64] = {};   // function attributes are per device
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
-    bool* attr_set = nullptr;
-    bool attr_local[2] = {false, false};
-    attr_set = (cur_dev >= 0 && cur_dev < 64) ? nullptr : attr_local;
-    const int which = L.dtype == PBL_F16 ? 0 : 1;
-    bool& attr_done = attr_set ? attr_set[which] : attr_set_dev[which][cur_dev];
+    bool attr_local = false;
+    bool& attr_done = (cur_dev >= 0 && cur_dev < 64) ? attr_set_dev[cur_dev] : attr_local;
+    (void)which;
     if (!attr_done) {
-        cudaError_t e = which == 0
-            ? cudaFuncSetAttribute(skinny_mma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-            : cudaFuncSetAttribute(skinny_mma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        int rc = check_cuda(e, "cudaFuncSetAttribute(skinny smem)");
+        int rc = check_cuda(cudaFuncSetAttribute(skinny_mma_kernel<T, kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                            "cudaFuncSetAttribute(skinny smem)");
         if (rc) return rc;
         attr_done = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(sk::kWarps * 32);
+    cfg.blockDim = dim3(kWarps * 32);
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -327,19 +351,24 @@ int launch_skinny(const Layer& L, const void* x, int64_t ldx, void* y, int64_t l
     cfg.numAttrs = pdl ? 1 : 0;
     const uint16_t* vals16 = (const uint16_t*)L.vals;
     const int Mi = (int)M, Ni = (int)L.N, Ki = (int)L.K, tci = (int)L.tiles_c, gi = (int)L.groups, tpg = L.tiles_per_group;
-    cudaError_t le;
-    if (which == 0) {
-        const __half* xx = (const __half*)x; __half* yy = (__half*)y;
-        le = cudaLaunchKernelEx(&cfg, skinny_mma_kernel<__half>, L.planes, L.vptr, vals16, L.affine, L.bias, xx, ldx, yy, ldy, Mi, Ni,
-                                Ki, tci, gi, tpg);
-    } else {
-        const __nv_bfloat16* xx = (const __nv_bfloat16*)x; __nv_bfloat16* yy = (__nv_bfloat16*)y;
-        le = cudaLaunchKernelEx(&cfg, skinny_mma_kernel<__nv_bfloat16>, L.planes, L.vptr, vals16, L.affine, L.bias, xx, ldx, yy, ldy,
-                                Mi, Ni, Ki, tci, gi, tpg);
-    }
-    if (le != cudaSuccess) { count_launch(); return check_cuda(le, "skinny launch"); }
+    const T* xx = (const T*)x;
+    T* yy = (T*)y;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, skinny_mma_kernel<T, kWarps>, L.planes, L.vptr, vals16, L.affine, L.bias, xx, ldx, yy,
+                                        ldy, Mi, Ni, Ki, tci, gi, tpg);
     count_launch();
-    return check_cuda(cudaGetLastError(), "skinny launch");
+    return check_cuda(le, "skinny launch");
+}
+
+int launch_skinny(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s) {
+    // 16 warps per CTA (one CTA per SM). 8-warp CTAs (two per SM) measured equal for N >= 11008 and slower for
+    // N = 4096 on B200 (profiles/r01 notes); PBL_SK_WARPS=8 keeps the variant reachable for experiments.
+    int warps = 16;
+    const char* e = getenv("PBL_SK_WARPS");
+    if (e && *e) warps = atoi(e) == 8 ? 8 : 16;
+    if (L.dtype == PBL_F16)
+        return warps == 8 ? launch_skinny_t<__half, 8>(L, x, ldx, y, ldy, M, s, 0) : launch_skinny_t<__half, 16>(L, x, ldx, y, ldy, M, s, 0);
+    return warps == 8 ? launch_skinny_t<__nv_bfloat16, 8>(L, x, ldx, y, ldy, M, s, 1)
+                      : launch_skinny_t<__nv_bfloat16, 16>(L, x, ldx, y, ldy, M, s, 1);
 }
 
 }  // namespace pbl
