@@ -233,6 +233,22 @@ def main():
     outs = [torch.empty(M, p.N, device=dev, dtype=torch.float16) for p in layers[0]]
     full_outs = [torch.empty(M, N, device=dev, dtype=torch.float16) for _, N, _, _ in SHAPES] if rowshard else None
 
+    # -- parity in the same run: CUDA path vs fp64 dense math over the bit-exact unpacked w_sim -------
+    parity = {}
+    if rank == 0:
+        for i in (0, 4, 6):                                   # the three distinct layer shapes
+            p = layers[0][i]
+            xs_ = xin[SHAPES[i][3]]
+            w64 = p.unpack().double()
+            for tag, rows in (("prefill", slice(0, 1024)), ("decode", slice(0, 8))):
+                yk = p.forward(xs_[rows].contiguous()).double()
+                ref = xs_[rows].double() @ w64.t()
+                parity[f"{SHAPES[i][0]}:{tag}"] = float((yk - ref).abs().max() / ref.abs().max())
+            del w64
+        parity["max_rel_err"] = max(parity.values())
+        parity["tolerance"] = 1e-3
+        assert parity["max_rel_err"] <= 1e-3, parity
+
     def step(x_h=None):
         for row in layers:
             for i, p in enumerate(row):
@@ -434,7 +450,7 @@ def main():
                            "packed_bytes": packed_bytes, "bits_per_weight": 8.0 * packed_bytes / nk * (world if rowshard else 1),
                            "salient_fraction": nnz / nk * (world if rowshard else 1), "model_build_s": build_s},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks_summary(samples), "roofline": roofline,
-                "cpu_baseline": cb, "decode": decode, "xnor_popcount": xnor}
+                "cpu_baseline": cb, "decode": decode, "xnor_popcount": xnor, "parity": parity}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
