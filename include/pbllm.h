@@ -148,7 +148,8 @@ PBL_API int pbl_bireal_forward(const pbl_layer* layer, const void* x, int64_t ld
 
 /* Which kernel pbl_linear_forward would launch for this (layer, M): 0 = CUDA-core bit-plane
  * kernel (fp32 I/O), 1 = tcgen05 bit-plane GEMM (M above PBL_SKINNY_MAX_M, default 16),
- * 2 = mma.sync bit-plane skinny kernel (decode).  PBL_FORCE_KERNEL=0|1|2 overrides (tests). */
+ * 2 = mma.sync bit-plane skinny kernel (decode), 3 = tcgen05 split-K cluster kernel (M <= 128).
+ * PBL_FORCE_KERNEL=0|1|2|3 overrides (tests). */
 PBL_API int pbl_select_kernel(const pbl_layer* layer, int64_t M);
 
 /* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */

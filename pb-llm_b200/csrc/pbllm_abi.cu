@@ -11,6 +11,11 @@
 #include "pbllm_common.cuh"
 
 namespace pbl {
+int launch_gemm_splitk(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s);
+bool gemm_splitk_supported(const Layer& L, const void* x, int64_t ldx, const void* y, int64_t ldy, int64_t M);
+}  // namespace pbl
+
+namespace pbl {
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
@@ -179,15 +184,25 @@ static int skinny_max_m() {
     return 16;
 }
 
-// 0 = CUDA-core bit-plane kernel, 1 = tcgen05 GEMM, 2 = mma.sync skinny kernel; -1 = forced kernel unsupported
+static int splitk_max_m() {   // M up to which the split-K cluster kernel is preferred (0 disables it)
+    const char* e = getenv("PBL_SPLITK_MAX_M");
+    if (e && *e) return atoi(e);
+    return 0;
+}
+
+// 0 = CUDA-core bit-plane kernel, 1 = tcgen05 GEMM (single-CTA / CTA-pair), 2 = mma.sync skinny kernel,
+// 3 = tcgen05 split-K cluster kernel (M <= 128); -1 = forced kernel unsupported
 static int select_impl(const Layer& L, const void* x, int64_t ldx, const void* y, int64_t ldy, int64_t M) {
     const bool tc_ok = gemm_tc_supported(L, x, ldx, y, ldy, M);
     const bool sk_ok = skinny_supported(L, M);
+    const bool ck_ok = gemm_splitk_supported(L, x, ldx, y, ldy, M);
     const int f = forced_kernel();
     if (f == 0) return 0;
     if (f == 1) return tc_ok ? 1 : -1;
     if (f == 2) return sk_ok ? 2 : -1;
+    if (f == 3) return ck_ok ? 3 : -1;
     if (!sk_ok) return 0;                       // fp32 I/O: CUDA cores
+    if (ck_ok && M <= splitk_max_m()) return 3;
     if (M <= skinny_max_m() || !tc_ok) return 2;
     return 1;
 }
@@ -216,6 +231,7 @@ int pbl_linear_forward(const pbl_layer* layer, const void* x, int64_t ldx, void*
     if (k < 0) { set_error("PBL_FORCE_KERNEL names a kernel that does not support this call"); return PBL_ERR_UNSUPPORTED; }
     if (k == 1) return launch_gemm_tc(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
     if (k == 2) return launch_skinny(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
+    if (k == 3) return launch_gemm_splitk(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
     return launch_gemv(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
 }
 

@@ -251,6 +251,32 @@ def test_gemm_tc_cta_pair_matches_oracle(dtype, N, K, gs, M, bias):
     assert torch.equal(y, y1)                                       # same tile, same k order: bit-identical to the 1-CTA kernel
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N,K,gs,M,bias", [(256, 64, -1, 1, False), (256, 256, -1, 8, True), (264, 520, -1, 16, True),
+                                           (100, 70, -1, 5, False), (768, 768, -1, 33, True), (512, 1024, 256, 64, False),
+                                           (4096, 4096, -1, 8, False), (11008, 4096, -1, 8, False), (4096, 11008, -1, 128, True),
+                                           (1024, 4096, -1, 100, False)])
+def test_gemm_splitk_cluster_matches_oracle(dtype, N, K, gs, M, bias):
+    """tcgen05 split-K cluster kernel (DSMEM reduction), incl. ragged shapes, every cluster size."""
+    w, low = synth_wsim(N, K, gs, dtype, seed=N + K + M)
+    b = rounded(np.random.RandomState(5).standard_normal(N).astype(np.float32) * 0.1, dtype) if bias else None
+    x = rounded(make_x(N * 13 + M, (M, K)), dtype)
+    p = pb.PackedLinear.from_dense(t(w, dtype), None if b is None else t(b, dtype), t(low), gs)
+    ref = orc.linear(x, w, b) if M * N * K <= 4e8 else \
+        (t(x).double() @ t(w).double().t() + (0 if b is None else t(b).double())).cpu().numpy()
+    ys = []
+    for C in ("", "1", "2", "3", "5", "8"):
+        if C:
+            os.environ["PBL_SPLITK_C"] = C
+        try:
+            y = forced(p, t(x, dtype), 3)
+        finally:
+            os.environ.pop("PBL_SPLITK_C", None)
+        assert relmax(y, ref) <= TOL[dtype], (C, relmax(y, ref))
+        ys.append(y)
+    assert torch.equal(ys[0], forced(p, t(x, dtype), 3))            # deterministic reduction order
+
+
 def test_gemm_tc_one_hot_activations_reproduce_w_sim_exactly():
     """x = I  =>  y = w_sim^T bit-for-bit: the expanded tile IS the reference's tensor."""
     w, low = synth_wsim(512, 256, -1, torch.float16, 77)
