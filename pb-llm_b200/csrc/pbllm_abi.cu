@@ -187,7 +187,7 @@ static int skinny_max_m() {
 static int splitk_max_m() {   // M up to which the split-K cluster kernel is preferred (0 disables it)
     const char* e = getenv("PBL_SPLITK_MAX_M");
     if (e && *e) return atoi(e);
-    return 0;
+    return 128;
 }
 
 // 0 = CUDA-core bit-plane kernel, 1 = tcgen05 GEMM (single-CTA / CTA-pair), 2 = mma.sync skinny kernel,
@@ -202,8 +202,9 @@ static int select_impl(const Layer& L, const void* x, int64_t ldx, const void* y
     if (f == 2) return sk_ok ? 2 : -1;
     if (f == 3) return ck_ok ? 3 : -1;
     if (!sk_ok) return 0;                       // fp32 I/O: CUDA cores
-    if (ck_ok && M <= splitk_max_m()) return 3;
-    if (M <= skinny_max_m() || !tc_ok) return 2;
+    if (M <= skinny_max_m()) return 2;          // decode: mma.sync skinny kernel (measured faster than split-K up to 16 tokens)
+    if (ck_ok && M <= splitk_max_m()) return 3; // short prompts: split-K cluster kernel (2x the single-CTA GEMM at M = 64)
+    if (!tc_ok) return 2;
     return 1;
 }
 

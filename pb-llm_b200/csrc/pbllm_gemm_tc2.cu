@@ -218,63 +218,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) 
 
             mbar_wait(empty(s), ph ^ 1u);
 
-            __syncwarp();
-            const uint32_t b0 = (cs * 2u) & ~15u;
-            {
-                const uint32_t o0 = 16u * lane, o1 = o0 + 512u;
-                if (b0 + o0 < ce * 2u) sts_v4(scratch + o0, v0.x, v0.y, v0.z, v0.w);
-                if (b0 + o1 < ce * 2u) sts_v4(scratch + o1, v1.x, v1.y, v1.z, v1.w);
-            }
-            __syncwarp();
-
             const uint32_t brow = smem_base + kOffB + s * kBStage + row_off;
-#pragma unroll
-            for (int wd = 0; wd < 2; ++wd) {
-                const uint32_t sg = wd ? pw.y : pw.x;
-                const uint32_t X0 = sg, X1 = sg << 1, X2 = sg << 2, X3 = sg << 3, X4 = sg << 4, X5 = sg << 5, X6 = sg << 6,
-                               X7 = sg << 7;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint32_t sel = 0x8888u | (uint32_t)c | ((uint32_t)c << 4) | ((uint32_t)(4 + c) << 8) | ((uint32_t)(4 + c) << 12);
-                    const uint32_t h0 = sel_xor_and(LL, DD, prmt(X7, X6, sel));
-                    const uint32_t h1 = sel_xor_and(LL, DD, prmt(X5, X4, sel));
-                    const uint32_t h2 = sel_xor_and(LL, DD, prmt(X3, X2, sel));
-                    const uint32_t h3 = sel_xor_and(LL, DD, prmt(X1, X0, sel));
-                    sts_v4(brow + ((((uint32_t)(wd * 4 + c)) ^ r7) << 4), h0, h1, h2, h3);
-                }
-            }
-            const uint32_t idx0 = (cs - (b0 >> 1)) + warp_excl_scan(__popc(pw.z) + __popc(pw.w), lane);
-            if (ce - (b0 >> 1) <= (uint32_t)kScratchVals) {
-                uint32_t sa = scratch + idx0 * 2u;
-#pragma unroll
-                for (int wd = 0; wd < 2; ++wd) {
-                    uint32_t rm = __brev(wd ? pw.w : pw.z);
-                    const uint32_t k1 = (r7 << 4) ^ (uint32_t)(wd * 64);
-                    while (rm) {
-                        const uint32_t j = (uint32_t)__clz(rm);
-                        rm &= ~(0x80000000u >> j);
-                        const uint16_t v = lds_u16(sa);
-                        sa += 2u;
-                        sts_u16(brow | ((j + j) ^ k1), v);
-                    }
-                }
-            } else {
-                uint32_t idx = idx0;
-#pragma unroll
-                for (int wd = 0; wd < 2; ++wd) {
-                    uint32_t mk = wd ? pw.w : pw.z;
-                    while (mk) {
-                        const uint32_t j = (uint32_t)__ffs(mk) - 1u;
-                        mk &= mk - 1u;
-                        uint16_t v;
-                        if (idx < (uint32_t)kScratchVals) v = lds_u16(scratch + idx * 2u);
-                        else v = __ldg(p.vals + (b0 >> 1) + idx);
-                        ++idx;
-                        const uint32_t col = (uint32_t)wd * 32u + j;
-                        sts_u16(brow + ((col << 1) ^ (r7 << 4)), v);
-                    }
-                }
-            }
+            expand_row(pw, LL, DD, brow, r7, cs, ce, v0, v1, scratch, p.vals, (uint32_t)lane);
             fence_proxy_async();          // this thread's generic-proxy writes -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(full_b_leader0 + 8u * s);   // one arrive per warp on the LEADER's barrier

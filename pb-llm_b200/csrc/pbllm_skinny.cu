@@ -14,7 +14,7 @@
 #include <cstdlib>
 #include <type_traits>
 
-#include "pbllm_common.cuh"
+#include "pbllm_tc_ptx.cuh"
 
 namespace pbl {
 
@@ -207,73 +207,12 @@ skinny_mma_kernel(const uint4* __restrict__ planes, const uint32_t* __restrict__
             }
         }
 
-        // ---- stage activations (row layout for the B fragments) and this row group's salient values
-        __syncwarp();
-        const uint32_t b0 = (cs * 2u) & ~15u;
-        {
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xr_st), "r"(xc0.x), "r"(xc0.y), "r"(xc0.z), "r"(xc0.w) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xr_st + 16u), "r"(xc1.x), "r"(xc1.y), "r"(xc1.z), "r"(xc1.w) : "memory");
-            const uint32_t o0 = 16u * lane, o1 = o0 + 512u;
-            if (b0 + o0 < ce * 2u) asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(scr + o0), "r"(v0.x), "r"(v0.y), "r"(v0.z), "r"(v0.w) : "memory");
-            if (b0 + o1 < ce * 2u) asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(scr + o1), "r"(v1.x), "r"(v1.y), "r"(v1.z), "r"(v1.w) : "memory");
-        }
-        __syncwarp();
-
-        // ---- rebuild my row (64 exact 16-bit values) in the warp's tile: dense {lo,hi} select ...
-#pragma unroll
-        for (int wd = 0; wd < 2; ++wd) {
-            const uint32_t sg = wd ? pw.y : pw.x;
-            const uint32_t X0 = sg, X1 = sg << 1, X2 = sg << 2, X3 = sg << 3, X4 = sg << 4, X5 = sg << 5, X6 = sg << 6,
-                           X7 = sg << 7;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const uint32_t sel = 0x8888u | (uint32_t)c | ((uint32_t)c << 4) | ((uint32_t)(4 + c) << 8) | ((uint32_t)(4 + c) << 12);
-                const uint32_t h0 = sk_sel(LL, DD, sk_prmt(X7, X6, sel));
-                const uint32_t h1 = sk_sel(LL, DD, sk_prmt(X5, X4, sel));
-                const uint32_t h2 = sk_sel(LL, DD, sk_prmt(X3, X2, sel));
-                const uint32_t h3 = sk_sel(LL, DD, sk_prmt(X1, X0, sel));
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(brow + ((((uint32_t)(wd * 4 + c)) ^ r7) << 4)), "r"(h0), "r"(h1),
-                             "r"(h2), "r"(h3)
-                             : "memory");
-            }
-        }
-        // ... then patch the salient values over their positions
-        if (__any_sync(0xffffffffu, (pw.z | pw.w) != 0u)) {
-            const uint32_t idx0 = (cs - (b0 >> 1)) + warp_excl_scan(__popc(pw.z) + __popc(pw.w), lane);
-            if (ce - (b0 >> 1) <= 512u) {            // warp-uniform: the whole chunk is staged in shared memory
-                uint32_t sa = scr + idx0 * 2u;
-#pragma unroll
-                for (int wd = 0; wd < 2; ++wd) {
-                    uint32_t rm = __brev(wd ? pw.w : pw.z);
-                    const uint32_t k1 = (r7 << 4) ^ (uint32_t)(wd * 64);
-                    while (rm) {
-                        const uint32_t j = (uint32_t)__clz(rm);
-                        rm &= ~(0x80000000u >> j);
-                        uint16_t v16;
-                        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v16) : "r"(sa) : "memory");
-                        sa += 2u;
-                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(brow | ((j + j) ^ k1)), "h"(v16) : "memory");
-                    }
-                }
-            } else {                                   // rare: very dense chunk, tail read from global
-                uint32_t idx = idx0;
-#pragma unroll
-                for (int wd = 0; wd < 2; ++wd) {
-                    uint32_t mk = wd ? pw.w : pw.z;
-                    while (mk) {
-                        const uint32_t j = (uint32_t)__ffs(mk) - 1u;
-                        mk &= mk - 1u;
-                        uint16_t v16;
-                        if (idx < 512u) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v16) : "r"(scr + idx * 2u) : "memory");
-                        else v16 = __ldg(vals + (b0 >> 1) + idx);
-                        ++idx;
-                        const uint32_t col = (uint32_t)wd * 32u + j;
-                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(brow + ((col << 1) ^ (r7 << 4))), "h"(v16) : "memory");
-                    }
-                }
-            }
-        }
-        __syncwarp();
+        // ---- stage activations (row layout for the B fragments), then rebuild my row of the exact tile ----
+        __syncwarp();                                   // previous iteration's ldmatrix / B-fragment reads are done
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xr_st), "r"(xc0.x), "r"(xc0.y), "r"(xc0.z), "r"(xc0.w) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xr_st + 16u), "r"(xc1.x), "r"(xc1.y), "r"(xc1.z), "r"(xc1.w) : "memory");
+        expand_row(pw, LL, DD, brow, r7, cs, ce, v0, v1, scr, vals, (uint32_t)lane);
+        __syncwarp();                                   // tile and activations visible to the whole warp
 
         // ---- tensor cores: A fragments by ldmatrix from the swizzled tile, B fragments from xr ------------
 #pragma unroll

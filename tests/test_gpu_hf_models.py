@@ -47,7 +47,7 @@ def test_hf_model_drop_in(make, method):
 
     hooks = [m.register_forward_hook(hook) for m in model.modules() if isinstance(m, pb.BinaryInterface)]
     with torch.no_grad():
-        logits = model(ids).logits                          # M = 128 tokens: tcgen05 path
+        logits = model(ids).logits                          # M = 128 tokens: tcgen05 split-K cluster path
         short = model(ids[:, :3]).logits                    # M = 6 tokens: mma.sync skinny path
     for h in hooks:
         h.remove()

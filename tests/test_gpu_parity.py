@@ -188,7 +188,7 @@ def test_gemm_tc_matches_oracle(dtype, N, K, gs, M, bias):
     b = rounded(np.random.RandomState(2).standard_normal(N).astype(np.float32) * 0.1, dtype) if bias else None
     x = rounded(make_x(N * 3 + M, (M, K)), dtype)
     p = pb.PackedLinear.from_dense(t(w, dtype), None if b is None else t(b, dtype), t(low), gs)
-    assert p.select_kernel(M) == (1 if M > 16 else 2)               # tcgen05 above the skinny threshold
+    assert p.select_kernel(M) == (2 if M <= 16 else (3 if M <= 128 else 1))   # skinny / split-K cluster / GEMM
     y = forced(p, t(x, dtype), 1)
     if M * N * K <= 4e8:
         ref = orc.linear(x, w, b)                                   # CPU oracle (double accumulate)
@@ -264,6 +264,12 @@ def test_gemm_splitk_cluster_matches_oracle(dtype, N, K, gs, M, bias):
     p = pb.PackedLinear.from_dense(t(w, dtype), None if b is None else t(b, dtype), t(low), gs)
     ref = orc.linear(x, w, b) if M * N * K <= 4e8 else \
         (t(x).double() @ t(w).double().t() + (0 if b is None else t(b).double())).cpu().numpy()
+    if K % 8 != 0:   # TMA needs 16 B-aligned activation rows: the forced kernel is refused, never silently replaced
+        with pytest.raises(RuntimeError, match="does not support"):
+            forced(p, t(x, dtype), 3)
+        assert p.select_kernel(M) == 2
+        return
+    assert p.select_kernel(M) == (2 if M <= 16 else 3)
     ys = []
     for C in ("", "1", "2", "3", "5", "8"):
         if C:
