@@ -194,7 +194,7 @@ __device__ __forceinline__ void expand_row(const uint4 pw, const uint32_t LL, co
         const uint32_t o0 = 16u * lane, o1 = o0 + 512u;
         if (b0 + o0 < ce * 2u) sts_v4(scratch + o0, v0.x, v0.y, v0.z, v0.w);
         if (b0 + o1 < ce * 2u) sts_v4(scratch + o1, v1.x, v1.y, v1.z, v1.w);
-        idx0 = (cs - (b0 >> 1)) + warp_excl_scan(npop, lane);   // issued early: its shuffle latency hides under the dense part
+        __syncwarp();                                    // staged values visible to every lane
     }
     // dense part: 64 bits -> 64 exact {lo,hi} values, 8 swizzled 16 B chunks
 #pragma unroll
@@ -212,8 +212,8 @@ __device__ __forceinline__ void expand_row(const uint4 pw, const uint32_t LL, co
         }
     }
     if (!any_sal) return;
-    __syncwarp();                                        // staged values visible to every lane
-    // salient part: patch the exact stored values over their positions (two per trip: two loads in flight)
+    idx0 = (cs - (b0 >> 1)) + warp_excl_scan(npop, lane);
+    // salient part: patch the exact stored values over their positions (a 2-way unrolled loop measured slower)
     if (ce - (b0 >> 1) <= 512u) {                        // warp-uniform: the whole chunk is staged in scratch
         uint32_t sa = scratch + idx0 * 2u;
 #pragma unroll
@@ -221,19 +221,11 @@ __device__ __forceinline__ void expand_row(const uint4 pw, const uint32_t LL, co
             uint32_t rm = __brev(wd ? pw.w : pw.z);      // msb-first: clz gives the lowest column
             const uint32_t k1 = (r7 << 4) ^ (uint32_t)(wd * 64);
             while (rm) {
-                const uint32_t j0 = (uint32_t)__clz(rm);
-                rm &= ~(0x80000000u >> j0);
-                const uint16_t a = lds_u16(sa);
-                if (rm) {
-                    const uint32_t j1 = (uint32_t)__clz(rm);
-                    rm &= ~(0x80000000u >> j1);
-                    const uint16_t b = lds_u16(sa + 2u);
-                    sa += 4u;
-                    sts_u16(brow | ((j1 + j1) ^ k1), b);
-                } else {
-                    sa += 2u;
-                }
-                sts_u16(brow | ((j0 + j0) ^ k1), a);
+                const uint32_t j = (uint32_t)__clz(rm);
+                rm &= ~(0x80000000u >> j);
+                const uint16_t v = lds_u16(sa);
+                sa += 2u;
+                sts_u16(brow | ((j + j) ^ k1), v);
             }
         }
     } else {                                             // rare: very dense chunk, tail read from global
