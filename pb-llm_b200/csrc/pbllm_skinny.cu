@@ -303,11 +303,15 @@ int launch_skinny(const Layer& L, const void* x, int64_t ldx, void* y, int64_t l
     // N = 4096 on B200 (profiles/r01 notes); PBL_SK_WARPS=8 keeps the variant reachable for experiments.
     int warps = 16;
     const char* e = getenv("PBL_SK_WARPS");
-    if (e && *e) warps = atoi(e) == 8 ? 8 : 16;
-    if (L.dtype == PBL_F16)
-        return warps == 8 ? launch_skinny_t<__half, 8>(L, x, ldx, y, ldy, M, s, 0) : launch_skinny_t<__half, 16>(L, x, ldx, y, ldy, M, s, 0);
-    return warps == 8 ? launch_skinny_t<__nv_bfloat16, 8>(L, x, ldx, y, ldy, M, s, 1)
-                      : launch_skinny_t<__nv_bfloat16, 16>(L, x, ldx, y, ldy, M, s, 1);
+    if (e && *e) { const int w = atoi(e); warps = (w == 8 || w == 24) ? w : 16; }
+    if (L.dtype == PBL_F16) {
+        if (warps == 8) return launch_skinny_t<__half, 8>(L, x, ldx, y, ldy, M, s, 0);
+        if (warps == 24) return launch_skinny_t<__half, 24>(L, x, ldx, y, ldy, M, s, 0);
+        return launch_skinny_t<__half, 16>(L, x, ldx, y, ldy, M, s, 0);
+    }
+    if (warps == 8) return launch_skinny_t<__nv_bfloat16, 8>(L, x, ldx, y, ldy, M, s, 1);
+    if (warps == 24) return launch_skinny_t<__nv_bfloat16, 24>(L, x, ldx, y, ldy, M, s, 1);
+    return launch_skinny_t<__nv_bfloat16, 16>(L, x, ldx, y, ldy, M, s, 1);
 }
 
 }  // namespace pbl
