@@ -505,3 +505,49 @@ def test_full_size_outlier_module_opt13b_shapes(N, K):
     y1 = m(x[:, :1])                                                                    # decode-sized call, skinny kernel
     assert float((y1.double().view(-1, N) - ref[:1]).abs().max() / ref[:1].abs().max()) <= 1e-3
     assert 1.0 < m.outlier_nbits < 2.0 and m.packed().bits_per_weight() < 4.0
+
+
+# ---- stress the rarely-taken paths of the expansion / packing -----------------------------------------------------
+@pytest.mark.parametrize("sal_frac", [0.0, 0.35, 0.6, 1.0])
+@pytest.mark.parametrize("M", [4, 40, 300, 700])
+def test_dense_salient_chunks_all_kernels(sal_frac, M):
+    """Salient density from none to every position: chunks larger than the 512-value staging buffer take the
+    global-memory tail path of expand_row; every kernel (skinny / split-K / GEMM / CTA pair) must still be exact."""
+    N, K, dtype = 320, 704, torch.float16
+    w, low = synth_wsim(N, K, -1, dtype, seed=int(sal_frac * 100) + M, sal_frac=sal_frac)
+    x = rounded(make_x(M + 17, (M, K)), dtype)
+    p = pb.PackedLinear.from_dense(t(w, dtype), None, t(low))
+    assert torch.equal(p.unpack(), t(w, dtype))
+    assert abs(p.nnz / (N * K) - sal_frac) < 0.02
+    ref = orc.linear(x, w)
+    y = p.forward(t(x, dtype))
+    assert relmax(y, ref) <= 1e-3, (p.select_kernel(M), relmax(y, ref))
+    os.environ["PBL_GEMM_2CTA"] = "2"
+    try:
+        assert relmax(forced(p, t(x, dtype), 1), ref) <= 1e-3
+    finally:
+        os.environ.pop("PBL_GEMM_2CTA")
+    if M <= 128:
+        assert relmax(forced(p, t(x, dtype), 3), ref) <= 1e-3
+    if M <= 40:
+        assert relmax(forced(p, t(x, dtype), 2), ref) <= 1e-3
+        assert relmax(forced(p, t(x, dtype), 0), ref) <= 1e-3
+
+
+def test_degenerate_rows_and_levels():
+    """Rows with a single level (lo == hi), all-zero rows, a row that is entirely salient, groupsize 64."""
+    N, K = 130, 256
+    rs = np.random.RandomState(9)
+    w = np.where(rs.rand(N, K) < 0.5, 0.0625, -0.03125).astype(np.float32)
+    w[0] = 0.25                      # one level only
+    w[1] = 0.0                       # all zeros (also one level)
+    w[2] = rs.standard_normal(K)     # nothing binarizable
+    w[3, ::2] = 0.5                  # three values in a row -> third value goes to the salient list
+    w = rounded(w, torch.float16)
+    x = rounded(make_x(3, (9, K)), torch.float16)
+    for gs in (-1, 64, 128):
+        p = pb.PackedLinear.from_dense(t(w, torch.float16), None, None, gs)
+        assert torch.equal(p.unpack(), t(w, torch.float16))
+        ref = orc.linear(x, w)
+        for kern in (0, 2, 3, 1):
+            assert relmax(forced(p, t(x, torch.float16), kern), ref) <= 1e-3, (gs, kern)
