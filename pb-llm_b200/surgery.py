@@ -76,6 +76,41 @@ def replace_from_fakequant(root_module: nn.Module, mask_dir: Optional[str] = Non
 
 
 @torch.no_grad()
+def from_reference(module: nn.Module, low_mask: Optional[torch.Tensor] = None, groupsize: int = -1):
+    """Pack straight from an instance of the REFERENCE's own module (any class of its quant/ package, or a
+    plain nn.Linear holding GPTQ-PB fake-quant weights): the effective weight is the tensor that module itself
+    would feed to F.linear, materialised by its own method on its own device and dtype -- the preferred
+    parity path (sign bits and scales are never recomputed here).
+      * XnorBinaryLinear / IrBinaryLinear / FdaBinaryLinear / BiRealLinear: `module.quant_weight()`
+      * BinaryXnorExceptOutliersLinear[Hessian]: `module.binarize_except_outliers()`, mask `~module.outlier_mask`
+      * BinaryLinear: `sign(weight)` (quant/quantizer.py:85);  nn.Linear: `weight` as is (+ optional mask file)
+    Returns a PackedFakeQuantLinear (BiReal keeps its XNOR-popcount forward through BiRealLinear)."""
+    name = type(module).__name__
+    bias = getattr(module, "bias", None)
+    if hasattr(module, "binarize_except_outliers"):
+        w_sim = module.binarize_except_outliers()
+        if low_mask is None and getattr(module, "outlier_mask", None) is not None:
+            low_mask = ~module.outlier_mask
+    elif hasattr(module, "quant_weight"):
+        w_sim = module.quant_weight()
+    elif name == "BinaryLinear":
+        w_sim = module.weight.data.sign()
+    elif isinstance(module, nn.Linear):
+        w_sim = module.weight.data
+    else:
+        raise TypeError(f"from_reference: don't know how {name} materialises its effective weight")
+    w_sim = w_sim.detach()
+    if name == "BiRealLinear":
+        q = _quant.BiRealLinear.__new__(_quant.BiRealLinear)
+        nn.Module.__init__(q)
+        q._init_params(module.weight, None, cast_fp32=True)
+        return q
+    q = _quant.PackedFakeQuantLinear(w_sim, bias, low_mask, groupsize)
+    q.global_name = getattr(module, "global_name", None)
+    return q
+
+
+@torch.no_grad()
 def pack_model(root_module: nn.Module, keep_latent: bool = False, verify: bool = False):
     """Pack every BinaryInterface module now (instead of lazily at first forward) and, by
     default, free the latent weights so the model occupies its packed size in HBM."""

@@ -122,3 +122,39 @@ def test_surgery_mirrors_reference(tmp_path):
     pb.replace_from_fakequant(m4, mask_dir=None)
     assert isinstance(m4.layers[1].q_proj, pb.PackedFakeQuantLinear)
     assert m4.layers[1].q_proj.weight.dtype == torch.float32   # dtype kept
+
+
+def test_from_reference_takes_the_modules_own_materialised_weight():
+    """Duck-typed stand-ins for the reference classes (the real ones cannot travel to the GPU box): the packed
+    module must be built from exactly the tensor the reference module itself returns."""
+    g = load("quantizer_small")
+
+    class XnorBinaryLinear(nn.Module):            # same method name / attributes as quant/quantizer.py:172-193
+        def __init__(self, w, b):
+            super().__init__()
+            self.weight, self.bias = nn.Parameter(w), nn.Parameter(b)
+
+        def quant_weight(self):
+            return t(g["wsim_Xnor"])
+
+    class BinaryXnorExceptOutliersLinear(nn.Module):   # quant/outlier_quantizer.py:33-106
+        def __init__(self, w):
+            super().__init__()
+            self.weight, self.bias = nn.Parameter(w), None
+            self.outlier_mask = t(g["W"]).abs() > 0.03
+            self.global_name = "m/layer"
+
+        def binarize_except_outliers(self):
+            return torch.where(self.outlier_mask, self.weight.data, self.weight.data.sign() * 0.01)
+
+    q = pb.from_reference(XnorBinaryLinear(t(g["W"]), t(g["b"])))
+    assert isinstance(q, pb.PackedFakeQuantLinear) and torch.equal(q.weight.data, t(g["wsim_Xnor"]))
+    assert torch.equal(q.bias.data, t(g["b"]))
+    ref = BinaryXnorExceptOutliersLinear(t(g["W"]))
+    q2 = pb.from_reference(ref)
+    assert torch.equal(q2.weight.data, ref.binarize_except_outliers()) and torch.equal(q2.low_mask, ~ref.outlier_mask)
+    assert q2.global_name == "m/layer"
+    q3 = pb.from_reference(nn.Linear(8, 4))
+    assert isinstance(q3, pb.PackedFakeQuantLinear)
+    with pytest.raises(TypeError):
+        pb.from_reference(nn.ReLU())
