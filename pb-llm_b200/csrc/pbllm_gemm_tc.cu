@@ -307,6 +307,7 @@ bool gemm_tc_supported(const Layer& L, const void* x, int64_t ldx, const void* y
 }
 
 int launch_gemm_tc(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s) {
+    if (gemm_twophase_enabled(L, M)) return launch_gemm_twophase(L, x, ldx, y, ldy, M, s);
     if (gemm_tc2_enabled(L, M)) return launch_gemm_tc2(L, x, ldx, y, ldy, M, s);
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled driver entry point unavailable"); return PBL_ERR_CUDA; }

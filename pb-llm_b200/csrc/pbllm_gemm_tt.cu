@@ -1,0 +1,333 @@
+// Two-phase prefill path: expand the packed weight ONCE into a dense fp16/bf16 scratch (L2-resident for the
+// usual layer sizes), then run a plain tcgen05 CTA-pair GEMM with BOTH operands fed by TMA.
+//
+// The fused kernels (pbllm_gemm_tc*.cu) re-expand a weight tile for every token tile that uses it; that is
+// free when the tensor pipe is the bottleneck (M >= ~8k tokens) but makes 256 < M < 4k expansion-bound.
+// Here the expansion cost is paid once per weight per call (kernel 1, HBM/L2-write bound, ~2*N*K bytes),
+// and kernel 2 is an ordinary K-major x K-major GEMM: TMA (SWIZZLE_128B) for x and for the scratch,
+// cta_group::2 UMMA M=256 N=256, fp32 accumulators in TMEM, same epilogue as gemm_tc2_kernel.
+// The scratch holds exactly w_sim (bit-identical to unpack()), so results match the fused kernels bit for bit.
+#include <cstdlib>
+#include <type_traits>
+
+#include "pbllm_tc_ptx.cuh"
+
+namespace pbl {
+
+// ---- kernel 1: packed -> dense scratch [n_pad][k_pad], K contiguous ---------------------------------------
+// CTA = one 128x64 plane tile; thread = weight row: expand_row into a swizzled smem tile, then coalesced
+// 16 B stores (8 lanes per 128 B row).
+template <typename T>
+__global__ void __launch_bounds__(128) expand_dense_kernel(const uint4* __restrict__ planes, const uint32_t* __restrict__ vptr,
+                                                           const uint16_t* __restrict__ vals, const float2* __restrict__ affine,
+                                                           int tiles_c, int groups, int tiles_per_group, uint16_t* __restrict__ out,
+                                                           int64_t k_pad) {
+    __shared__ __align__(1024) uint8_t tile[kTileRows * 128];
+    __shared__ __align__(16) uint8_t scr[4][1024];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, r = threadIdx.x;
+    const int64_t t = blockIdx.x;
+    const int64_t tr = t / tiles_c, tc = t % tiles_c;
+    const uint4 pw = __ldg(planes + t * kTileRows + r);
+    const uint32_t cs = __ldg(vptr + t * kRgPerTile + wid), ce = __ldg(vptr + t * kRgPerTile + wid + 1);
+    const float2 a = __ldg(affine + (tr * kTileRows + r) * groups + tc / tiles_per_group);
+    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = make_uint4(0, 0, 0, 0);
+    {
+        const uint32_t b0 = (cs * 2u) & ~15u, b1 = ce * 2u;
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(vals);
+        const uint32_t o0 = b0 + 16u * lane, o1 = o0 + 512u;
+        if (o0 < b1) v0 = __ldg(reinterpret_cast<const uint4*>(base + o0));
+        if (o1 < b1) v1 = __ldg(reinterpret_cast<const uint4*>(base + o1));
+    }
+    const uint32_t lo = bits16<T>(a.x), hi = bits16<T>(a.y);
+    const uint32_t tile_s = smem_u32(tile);
+    const uint32_t r7 = (uint32_t)(r & 7);
+    expand_row(pw, lo | (lo << 16), (lo ^ hi) * 0x10001u, tile_s + (uint32_t)r * 128u, r7, cs, ce, v0, v1, smem_u32(scr[wid]), vals,
+               (uint32_t)lane);
+    __syncthreads();
+    // copy out: 128 rows x 8 chunks of 16 B; consecutive threads take consecutive chunks of a row
+    uint16_t* dst = out + (tr * kTileRows) * k_pad + tc * kTileCols;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int idx = i * 128 + threadIdx.x;
+        const int row = idx >> 3, c = idx & 7;
+        const uint4 v = *reinterpret_cast<const uint4*>(tile + row * 128 + ((c ^ (row & 7)) << 4));
+        *reinterpret_cast<uint4*>(dst + (int64_t)row * k_pad + c * 8) = v;
+    }
+}
+
+namespace tt {
+constexpr int BMC = 256, BN = 256, BNC = 128, BK = 64;
+constexpr int kStages = 4;
+constexpr int kAStage = BMC * BK * 2;  // 32 KB
+constexpr int kBStage = BNC * BK * 2;  // 16 KB
+constexpr int kEpiWarps = 4;
+constexpr int kThreads = (2 + kEpiWarps) * 32;  // 192
+constexpr int kOffA = 0;
+constexpr int kOffB = kOffA + kStages * kAStage;
+constexpr int kOffBar = kOffB + kStages * kBStage;
+constexpr int kNumBars = 2 * kStages + 2;
+constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
+constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;
+static_assert(kSmemBytes <= 232448, "exceeds 227 KB");
+}  // namespace tt
+
+// ---- kernel 2: plain CTA-pair tcgen05 GEMM, A = x (TMA), B = dense scratch (TMA) --------------------------------
+template <typename T>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tt::kThreads, 1)
+gemm_tt_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
+    using namespace tt;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const bool leader = crank == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    const uint32_t bar0 = smem_base + kOffBar;
+    auto full = [&](int s) { return bar0 + 8u * s; };                        // leader only: A+B bytes of both CTAs
+    auto empty = [&](int s) { return bar0 + 8u * (kStages + s); };           // one per CTA (multicast commit)
+    const uint32_t tmem_full = bar0 + 8u * (2 * kStages);
+    const uint32_t tmem_empty = bar0 + 8u * (2 * kStages + 1);
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + kOffTmemPtr);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 2 * kEpiWarps);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + kOffTmemPtr), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_tiles = p.m_tiles * p.n_tiles;
+    const int my_tiles = (num_tiles - cluster_id + num_clusters - 1) / num_clusters;
+    const int KB = p.kblocks;
+    const uint32_t stage_bytes = (uint32_t)p.bm * 128u + 2u * kBStage;       // both CTAs: x boxes + weight boxes
+
+    if (warp == 0) {
+        // ===== TMA producer: this CTA's x tile and its half of the weight tile; bytes complete on the leader =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+            int s = 0;
+            uint32_t ph = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int t = cluster_id + ti * num_clusters;
+                const int m0 = (t / p.n_tiles) * p.bm + (int)crank * (p.bm >> 1);
+                const int n0 = (t % p.n_tiles) * BN + (int)crank * BNC;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(empty(s), ph ^ 1u);
+                    if (leader) mbar_arrive_expect_tx(full(s), stage_bytes);
+                    const uint32_t fb = full(s) & 0xFEFFFFFFu;
+                    tma_load_2d_2sm(smem_base + kOffA + s * kAStage, &tmap_x, kb * BK, m0, fb);
+                    tma_load_2d_2sm(smem_base + kOffB + s * kBStage, &tmap_w, kb * BK, n0, fb);
+                    if (++s == kStages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader only) =====
+        if (leader) {
+            const uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((256u >> 4) << 24);
+            int s = 0;
+            uint32_t ph = 0, acc_ph = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int t = cluster_id + ti * num_clusters;
+                const int m0 = (t / p.n_tiles) * p.bm;
+                const int halves = (p.bm == 2 * BMC && m0 + 128 < p.M) ? 2 : 1;
+                mbar_wait_cluster(tmem_empty, acc_ph ^ 1u);
+                tc_fence_after();
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait_cluster(full(s), ph);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a_addr = smem_base + kOffA + s * kAStage, b_addr = smem_base + kOffB + s * kBStage;
+                        for (int h = 0; h < halves; ++h) {
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                umma_f16_2sm(tmem_base + h * 256, make_sw128_desc(a_addr + h * (128 * 128) + k * 32),
+                                             make_sw128_desc(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit_2sm(empty(s));
+                        if (kb == KB - 1) umma_commit_2sm(tmem_full);
+                    }
+                    __syncwarp();
+                    if (++s == kStages) { s = 0; ph ^= 1u; }
+                }
+                acc_ph ^= 1u;
+            }
+        }
+    } else {
+        // ===== epilogue: this CTA's 256 tokens x 256 weight rows (TMEM -> regs -> +bias -> 16 bit -> global) =====
+        const int q = warp & 3;
+        uint32_t acc_ph = 0;
+        T* y = reinterpret_cast<T*>(p.y);
+        const uint32_t tmem_empty_leader = mapa_rank0(tmem_empty);
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int t = cluster_id + ti * num_clusters;
+            const int mp = (t / p.n_tiles) * p.bm;
+            const int m0 = mp + (int)crank * (p.bm >> 1), n0 = (t % p.n_tiles) * BN;
+            const int halves = (p.bm == 2 * BMC && mp + 128 < p.M) ? 2 : 1;      // which accumulators the MMA warp wrote
+            mbar_wait(tmem_full, acc_ph);
+            tc_fence_after();
+            for (int h = 0; h < halves; ++h) {
+                const int m = m0 + h * 128 + q * 32 + lane;
+                if (m0 + h * 128 >= p.M) break;                // warp-uniform: no valid token in this half
+#pragma unroll 1
+                for (int cb = 0; cb < BN / 32; ++cb) {
+                    const int n = n0 + cb * 32;
+                    if (n >= p.N) break;
+                    uint32_t acc[32];
+                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256 + cb * 32), acc);
+                    tmem_ld_wait();
+                    if (m < p.M) {
+                        T* yrow = y + (int64_t)m * p.ldy + n;
+#pragma unroll
+                        for (int v8 = 0; v8 < 4; ++v8) {
+                            if (n + v8 * 8 + 8 <= p.N) {
+                                float f[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(acc[v8 * 8 + i]);
+                                if (p.bias) {
+                                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n + v8 * 8));
+                                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + v8 * 8 + 4));
+                                    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                                    f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                                }
+                                uint4 o;
+                                o.x = pack2<T>(f[0], f[1]); o.y = pack2<T>(f[2], f[3]);
+                                o.z = pack2<T>(f[4], f[5]); o.w = pack2<T>(f[6], f[7]);
+                                *reinterpret_cast<uint4*>(yrow + v8 * 8) = o;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
+            acc_ph ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+static int twophase_mode() {   // PBL_TWOPHASE: 0 = never, 1 = where measured faster (default), 2 = for every M > 256
+    const char* e = getenv("PBL_TWOPHASE");
+    return (e && *e) ? atoi(e) : 1;
+}
+
+bool gemm_twophase_enabled(const Layer& L, int64_t M) {
+    const int mode = twophase_mode();
+    if (mode == 0 || M <= 256) return false;
+    if (mode == 2) return true;
+    (void)L;
+    return M < 8192;   // below this the fused kernels are expansion-bound
+}
+
+int launch_gemm_twophase(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled driver entry point unavailable"); return PBL_ERR_CUDA; }
+    static int num_sms = 0;
+    static bool pool_set = false;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!num_sms) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!pool_set) {   // keep freed scratch cached in the stream-ordered pool instead of returning it to the OS
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        (void)cudaGetLastError();
+        pool_set = true;
+    }
+    const size_t scratch_bytes = (size_t)L.n_pad * (size_t)L.k_pad * 2;
+    void* scratch = nullptr;
+    int rc = check_cuda(cudaMallocAsync(&scratch, scratch_bytes, s), "cudaMallocAsync(weight scratch)");
+    if (rc) return rc;
+
+    const int which = L.dtype == PBL_F16 ? 0 : 1;
+    const unsigned tiles = (unsigned)(L.tiles_r * L.tiles_c);
+    if (which == 0)
+        expand_dense_kernel<__half><<<tiles, 128, 0, s>>>(L.planes, L.vptr, (const uint16_t*)L.vals, L.affine, (int)L.tiles_c,
+                                                         (int)L.groups, L.tiles_per_group, (uint16_t*)scratch, L.k_pad);
+    else
+        expand_dense_kernel<__nv_bfloat16><<<tiles, 128, 0, s>>>(L.planes, L.vptr, (const uint16_t*)L.vals, L.affine, (int)L.tiles_c,
+                                                                 (int)L.groups, L.tiles_per_group, (uint16_t*)scratch, L.k_pad);
+    count_launch();
+    rc = check_cuda(cudaGetLastError(), "expand_dense launch");
+    if (rc) { cudaFreeAsync(scratch, s); return rc; }
+
+    const int n_tiles = (int)((L.N + tt::BN - 1) / tt::BN);
+    const int bm = (((M + 511) / 512) * (int64_t)n_tiles >= num_sms / 2) ? 512 : 256;
+    const CUtensorMapDataType dt = L.dtype == PBL_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const cuuint32_t estr[2] = {1, 1};
+    CUtensorMap tmx, tmw;
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)L.K, (cuuint64_t)M};
+        const cuuint64_t gstr[1] = {(cuuint64_t)ldx * 2};
+        const cuuint32_t box[2] = {(cuuint32_t)tt::BK, (cuuint32_t)(bm / 2)};
+        CUresult cr = enc(&tmx, dt, 2, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) { cudaFreeAsync(scratch, s); set_error("cuTensorMapEncodeTiled(x) failed (%d)", (int)cr); return PBL_ERR_CUDA; }
+    }
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)L.k_pad, (cuuint64_t)L.n_pad};
+        const cuuint64_t gstr[1] = {(cuuint64_t)L.k_pad * 2};
+        const cuuint32_t box[2] = {(cuuint32_t)tt::BK, (cuuint32_t)tt::BNC};
+        CUresult cr = enc(&tmw, dt, 2, scratch, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) { cudaFreeAsync(scratch, s); set_error("cuTensorMapEncodeTiled(w) failed (%d)", (int)cr); return PBL_ERR_CUDA; }
+    }
+    GemmParams p;
+    p.planes = L.planes; p.vptr = L.vptr; p.vals = reinterpret_cast<const uint16_t*>(L.vals); p.affine = L.affine;
+    p.bias = L.bias; p.y = y; p.ldy = ldy; p.M = (int)M; p.N = (int)L.N; p.K = (int)L.K;
+    p.tiles_r = (int)L.tiles_r; p.tiles_c = (int)L.tiles_c; p.groups = (int)L.groups; p.tiles_per_group = L.tiles_per_group;
+    p.bm = bm;
+    p.m_tiles = (int)((M + bm - 1) / bm);
+    p.n_tiles = n_tiles;
+    p.kblocks = (int)L.tiles_c;
+
+    static bool attr_set_dev[2][64] = {};
+    auto kern = which == 0 ? gemm_tt_kernel<__half> : gemm_tt_kernel<__nv_bfloat16>;
+    bool attr_local = false;
+    bool& attr_done = (dev >= 0 && dev < 64) ? attr_set_dev[which][dev] : attr_local;
+    if (!attr_done) {
+        rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tt::kSmemBytes),
+                        "cudaFuncSetAttribute(smem, tt)");
+        if (rc) { cudaFreeAsync(scratch, s); return rc; }
+        attr_done = true;
+    }
+    const int ntiles = p.m_tiles * p.n_tiles;
+    const int max_clusters = num_sms / 2;
+    const int clusters = ntiles < max_clusters ? ntiles : max_clusters;
+    kern<<<2 * clusters, tt::kThreads, tt::kSmemBytes, s>>>(tmx, tmw, p);
+    count_launch();
+    rc = check_cuda(cudaGetLastError(), "gemm_tt launch");
+    cudaError_t fe = cudaFreeAsync(scratch, s);
+    if (!rc) rc = check_cuda(fe, "cudaFreeAsync(weight scratch)");
+    return rc;
+}
+
+}  // namespace pbl

@@ -266,6 +266,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn get_encode_fn();
 int launch_gemm_tc2(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s);
 bool gemm_tc2_enabled(const Layer& L, int64_t M);
+int launch_gemm_twophase(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s);
+bool gemm_twophase_enabled(const Layer& L, int64_t M);
 int launch_gemm_splitk(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s);
 bool gemm_splitk_supported(const Layer& L, const void* x, int64_t ldx, const void* y, int64_t ldy, int64_t M);
 

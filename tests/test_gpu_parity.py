@@ -283,6 +283,28 @@ def test_gemm_splitk_cluster_matches_oracle(dtype, N, K, gs, M, bias):
     assert torch.equal(ys[0], forced(p, t(x, dtype), 3))            # deterministic reduction order
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N,K,gs,M,bias", [(256, 64, -1, 300, False), (264, 520, -1, 700, True), (768, 768, -1, 1000, True),
+                                           (512, 1024, 256, 513, False), (4096, 4096, -1, 2048, False), (1024, 11008, -1, 600, True)])
+def test_gemm_two_phase_matches_fused(dtype, N, K, gs, M, bias):
+    """expand-once + TMA/TMA GEMM: the scratch is exactly w_sim, so results equal the fused kernels bit for bit."""
+    w, low = synth_wsim(N, K, gs, dtype, seed=N + K + M)
+    b = rounded(np.random.RandomState(6).standard_normal(N).astype(np.float32) * 0.1, dtype) if bias else None
+    x = rounded(make_x(N * 17 + M, (M, K)), dtype)
+    p = pb.PackedLinear.from_dense(t(w, dtype), None if b is None else t(b, dtype), t(low), gs)
+    ref = orc.linear(x, w, b) if M * N * K <= 4e8 else \
+        (t(x).double() @ t(w).double().t() + (0 if b is None else t(b).double())).cpu().numpy()
+    outs = {}
+    for mode in ("2", "0"):
+        os.environ["PBL_TWOPHASE"] = mode
+        try:
+            outs[mode] = forced(p, t(x, dtype), 1)
+        finally:
+            os.environ.pop("PBL_TWOPHASE")
+        assert relmax(outs[mode], ref) <= TOL[dtype], (mode, relmax(outs[mode], ref))
+    assert torch.equal(outs["2"], outs["0"])
+
+
 def test_gemm_tc_one_hot_activations_reproduce_w_sim_exactly():
     """x = I  =>  y = w_sim^T bit-for-bit: the expanded tile IS the reference's tensor."""
     w, low = synth_wsim(512, 256, -1, torch.float16, 77)
