@@ -311,15 +311,18 @@ def main():
     pk = peaks()
     kernel_id = layers[0][0].select_kernel(M)
     # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/
-    # r01_gemm_tc2_cta_pair_M16384_N4096_K4096.md): dram read 145.0 MB + write 95.8 MB for the
-    # q/k/v/o-shaped launch (algorithmic: 134 MB x + 134 MB y + 7.6 MB packed weights; part of y is
-    # still in L2 when the capture window closes).
-    ncu_traffic = {"launch": "M=16384 N=4096 K=4096", "bytes": 145.033216e6 + 95.770368e6, "algorithmic_bytes": 2 * 16384 * 4096 * 2 + 7.6e6}
+    # r01_gemm_two_phase_M16384_N4096_K4096.md): gemm_tt_kernel dram read 264.7 MB + write 109.3 MB for the
+    # q/k/v/o-shaped launch (algorithmic: 134 MB x + 134 MB y + 7.6 MB packed weights; the 33.5 MB dense
+    # scratch written by expand_dense_kernel stays in L2 -- its own dram write is 0.02 MB -- but is partly
+    # re-fetched by the GEMM waves, as is x).
+    ncu_traffic = {"launch": "M=16384 N=4096 K=4096 (gemm_tt_kernel)", "bytes": 264.709376e6 + 109.28e6,
+                   "algorithmic_bytes": 2 * 16384 * 4096 * 2 + 7.6e6}
     roofline = None
     if per:
         ach = flops / (kern_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"],
-                    "traffic": ncu_traffic["bytes"] if (kernel_id == 1 and M >= 2048) else None, "traffic_note": ncu_traffic, "kernel": {0: "pbl CUDA-core bit-plane kernel", 1: "pbl tcgen05 bit-plane GEMM", 2: "pbl mma.sync bit-plane skinny kernel"}[kernel_id],
+                    "traffic": ncu_traffic["bytes"] if (kernel_id == 1 and M >= 2048) else None, "traffic_note": ncu_traffic, "kernel": {0: "pbl CUDA-core bit-plane kernel", 1: "pbl two-phase prefill: expand_dense_kernel + gemm_tt_kernel (tcgen05 cta_group::2, TMA both operands); times include both launches",
+                               2: "pbl mma.sync bit-plane skinny kernel", 3: "pbl tcgen05 split-K cluster kernel"}[kernel_id],
                     "launches": len(per), "avg_launch_ms": kern_ms / len(per), "peak_source": pk["src"] + ", sustained bf16",
                     "frac_of_burst_peak": ach / pk["tf_burst"],
                     "algorithmic_flops_per_launch": "2*M*N*K (M=tokens/step, N,K of the linear)"}
