@@ -71,6 +71,19 @@ constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;
 static_assert(kSmemBytes <= 232448, "exceeds 227 KB");
 }  // namespace tt
 
+// Tile rasterisation: n-tiles are taken in groups of kGroupN; inside a group the tile index runs n-fastest, so
+// the ~74 pair tiles in flight share one 8 x 256-row weight slab (<= 17 MB at K = 4096) and a few token tiles:
+// the slab stays in L2 across the group's waves instead of the whole scratch (90 MB for 11008 x 4096) being
+// re-fetched from HBM every wave.
+constexpr int kGroupN = 8;
+__device__ __forceinline__ void tile_mn(int t, const GemmParams& p, int& m_tile, int& n_tile) {
+    const int per_group = kGroupN * p.m_tiles;
+    const int g = t / per_group, r = t - g * per_group;
+    const int gn = min(kGroupN, p.n_tiles - g * kGroupN);
+    m_tile = r / gn;
+    n_tile = g * kGroupN + (r - m_tile * gn);
+}
+
 // ---- kernel 2: plain CTA-pair tcgen05 GEMM, A = x (TMA), B = dense scratch (TMA) --------------------------------
 template <typename T>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tt::kThreads, 1)
@@ -124,9 +137,10 @@ gemm_tt_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             int s = 0;
             uint32_t ph = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
-                const int t = cluster_id + ti * num_clusters;
-                const int m0 = (t / p.n_tiles) * p.bm + (int)crank * (p.bm >> 1);
-                const int n0 = (t % p.n_tiles) * BN + (int)crank * BNC;
+                int mt, nt;
+                tile_mn(cluster_id + ti * num_clusters, p, mt, nt);
+                const int m0 = mt * p.bm + (int)crank * (p.bm >> 1);
+                const int n0 = nt * BN + (int)crank * BNC;
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(empty(s), ph ^ 1u);
                     if (leader) mbar_arrive_expect_tx(full(s), stage_bytes);
@@ -145,8 +159,9 @@ gemm_tt_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             int s = 0;
             uint32_t ph = 0, acc_ph = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
-                const int t = cluster_id + ti * num_clusters;
-                const int m0 = (t / p.n_tiles) * p.bm;
+                int mt, nt;
+                tile_mn(cluster_id + ti * num_clusters, p, mt, nt);
+                const int m0 = mt * p.bm;
                 const int halves = (p.bm == 2 * BMC && m0 + 128 < p.M) ? 2 : 1;
                 mbar_wait_cluster(tmem_empty, acc_ph ^ 1u);
                 tc_fence_after();
@@ -177,9 +192,10 @@ gemm_tt_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         T* y = reinterpret_cast<T*>(p.y);
         const uint32_t tmem_empty_leader = mapa_rank0(tmem_empty);
         for (int ti = 0; ti < my_tiles; ++ti) {
-            const int t = cluster_id + ti * num_clusters;
-            const int mp = (t / p.n_tiles) * p.bm;
-            const int m0 = mp + (int)crank * (p.bm >> 1), n0 = (t % p.n_tiles) * BN;
+            int mt, nt;
+            tile_mn(cluster_id + ti * num_clusters, p, mt, nt);
+            const int mp = mt * p.bm;
+            const int m0 = mp + (int)crank * (p.bm >> 1), n0 = nt * BN;
             const int halves = (p.bm == 2 * BMC && mp + 128 < p.M) ? 2 : 1;      // which accumulators the MMA warp wrote
             mbar_wait(tmem_full, acc_ph);
             tc_fence_after();
