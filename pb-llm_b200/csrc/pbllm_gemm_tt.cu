@@ -248,7 +248,7 @@ gemm_tt_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
-static int twophase_mode() {   // PBL_TWOPHASE: 0 = never (fused kernels only), otherwise for every M > 256 (default)
+static int twophase_mode() {   // PBL_TWOPHASE: 0 = never (fused kernels only), otherwise for every M > 128 (default)
     const char* e = getenv("PBL_TWOPHASE");
     return (e && *e) ? atoi(e) : 1;
 }
@@ -257,7 +257,7 @@ bool gemm_twophase_enabled(const Layer& L, int64_t M) {
     (void)L;
     // measured faster than the fused CTA-pair kernel for every M > 256 on B200: 38 vs 49 us at M=512,
     // 69 vs 94 us at M=2048, 389 vs 437 us at M=16384 (4096x4096), 1136 vs 1162 us (11008x4096)
-    return twophase_mode() != 0 && M > 256;
+    return twophase_mode() != 0 && M > 128;
 }
 
 int launch_gemm_twophase(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s) {
