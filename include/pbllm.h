@@ -124,7 +124,11 @@ PBL_API int pbl_unpack(const pbl_layer* layer, void* w_out, int64_t ldw, void* s
 /* y[m][i] = sum_j x[m][j] * w_sim[i][j] + bias[i]   (fp32 accumulation, y rounded to dtype)
  * Replaces F.linear(x, w_sim, bias) at quant/quantizer.py:86,193 and
  * quant/outlier_quantizer.py:105.  x: device [M][ldx], y: device [M][ldy] (row-major, dtype).
- * M = product of the leading dims of the reference's x[..., K].  M == 0 is a no-op. */
+ * M = product of the leading dims of the reference's x[..., K].  M == 0 is a no-op.
+ * For fp16/bf16 and M > 128 the weight is first expanded into a transient dense scratch of
+ * 2*n_pad*k_pad bytes taken from (and returned to) the device's stream-ordered memory pool on `stream`
+ * (cudaMallocAsync / cudaFreeAsync: no synchronisation, CUDA-graph capturable); PBL_TWOPHASE=0 selects the
+ * fused kernels that need no scratch. */
 PBL_API int pbl_linear_forward(const pbl_layer* layer, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M,
                        void* stream);
 
