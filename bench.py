@@ -224,6 +224,7 @@ def main():
     torch.cuda.synchronize()
     build_s = time.time() - t0
     packed_bytes = sum(p.packed_bytes() for row in layers for p in row)
+    dindex_bytes = sum(p.decode_index_bytes() for row in layers for p in row)
     nnz = sum(p.nnz for row in layers for p in row)
     nk = sum(N * K for _, N, K, _ in SHAPES) * args.layers
 
@@ -322,7 +323,8 @@ def main():
         ach = flops / (kern_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"],
                     "traffic": ncu_traffic["bytes"] if (kernel_id == 1 and M >= 2048) else None, "traffic_note": ncu_traffic, "kernel": {0: "pbl CUDA-core bit-plane kernel", 1: "pbl two-phase prefill: expand_dense_kernel + gemm_tt_kernel (tcgen05 cta_group::2, TMA both operands); times include both launches",
-                               2: "pbl mma.sync bit-plane skinny kernel", 3: "pbl tcgen05 split-K cluster kernel"}[kernel_id],
+                               2: "pbl mma.sync bit-plane skinny kernel", 3: "pbl tcgen05 split-K cluster kernel",
+                               4: "pbl decode kernel"}[kernel_id],
                     "launches": len(per), "avg_launch_ms": kern_ms / len(per), "peak_source": pk["src"] + ", sustained bf16",
                     "frac_of_burst_peak": ach / pk["tf_burst"],
                     "algorithmic_flops_per_launch": "2*M*N*K (M=tokens/step, N,K of the linear)"}
@@ -420,12 +422,14 @@ def main():
         ach = (b_bin + b_sal) / (ms_d * 1e-3) / 1e9
         decode = {"tokens_per_s": Md * (1 if rowshard else world) / (ms_d * 1e-3), "ms_per_step": ms_d,
                   "ms_per_step_eager_python_launch": ms_d_eager, "batch": Md, "ms_per_step_batch1": ms_d1,
-                  "batch1_actual_bytes_gbs": packed_bytes / (ms_d1 * 1e-3) / 1e9,
+                  "batch1_actual_bytes_gbs": (dindex_bytes if layers[0][0].select_kernel(1) == 4 else packed_bytes) / (ms_d1 * 1e-3) / 1e9,
                   "ms_per_step_fused_siblings": ms_d_fused, "launch": "CUDA graph replay of the 224 launches",
-                  "kernel": "pbl mma.sync bit-plane skinny kernel" if layers[0][0].select_kernel(Md) == 2 else "pbl CUDA-core bit-plane kernel",
+                  "kernel": {4: "pbl decode kernel (positioned salient entries, warp-granular stream-K, mma.sync)",
+                             2: "pbl mma.sync bit-plane skinny kernel"}.get(layers[0][0].select_kernel(Md), "pbl CUDA-core bit-plane kernel"),
                   "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                                "traffic": None, "algorithmic_bytes_per_step": b_bin + b_sal,
-                               "actual_packed_bytes": packed_bytes, "actual_bytes_gbs": packed_bytes / (ms_d * 1e-3) / 1e9,
+                               "actual_packed_bytes": packed_bytes, "decode_index_bytes": dindex_bytes,
+                               "actual_bytes_gbs": (dindex_bytes if layers[0][0].select_kernel(Md) == 4 else packed_bytes) / (ms_d * 1e-3) / 1e9,
                                "peak_source": pk["src"]}}
 
     # -- the literal XNOR-popcount kernel (BiRealLinear format: alpha*sign(W), binarized activations) ---------------
@@ -482,7 +486,7 @@ def main():
                 "config": {"workload": workload_name(args), "tokens_per_step_per_gpu": M,
                            "parallelism": (f"rowshard{world}+allgather" if rowshard else f"dp{world} (replicas, no collective)"),
                            "l2": "per-step working set (2.3 GB packed weights + activations) >> 126 MB L2; no flush needed",
-                           "packed_bytes": packed_bytes, "bits_per_weight": 8.0 * packed_bytes / nk * (world if rowshard else 1),
+                           "packed_bytes": packed_bytes, "decode_index_bytes": dindex_bytes, "bits_per_weight": 8.0 * packed_bytes / nk * (world if rowshard else 1),
                            "salient_fraction": nnz / nk * (world if rowshard else 1), "model_build_s": build_s},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks_summary(samples), "roofline": roofline,
                 "cpu_baseline": cb, "decode": decode, "xnor_popcount": xnor, "parity": parity}

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PBL_ABI_VERSION 2
+#define PBL_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define PBL_API __attribute__((visibility("default")))
@@ -140,6 +140,32 @@ PBL_API size_t pbl_forward_host_workspace(const pbl_layer* layer, int64_t M);
 PBL_API int pbl_linear_forward_host(const pbl_layer* layer, const void* x_host, void* y_host, int64_t M, void* workspace,
                             void* stream);
 
+/* ---- decode index (optional, fp16 / bf16 layers): a second, row-group-major view of the packed layer with an
+ *      explicit tile position per salient entry, built once from the packed buffers.  With it attached,
+ *      pbl_linear_forward[_ws] routes calls of M <= 16 tokens (the per-token step of generation, where the
+ *      reference's F.linear re-reads the whole dense weight: quant/quantizer.py:86,193, outlier_quantizer.py:105)
+ *      to the decode kernel.  Sizes: dsign = blocks*32*8 bytes, eptr = (blocks+1)*4 bytes, ent = 16 bytes per
+ *      unit, units = eptr[blocks] after pbl_decode_index_count (read it back to size `ent`). ---- */
+typedef struct {
+    int64_t blocks;      /* (n_pad/32) * tiles_c blocks of 32 rows x 64 columns */
+    size_t dsign_bytes;  /* uint2 [blocks][32] sign words */
+    size_t eptr_bytes;   /* u32 [blocks + 1] entry offsets in 16-byte units */
+} pbl_decode_sizes;
+PBL_API int pbl_decode_index_sizes(const pbl_layer* layer, pbl_decode_sizes* out);
+PBL_API int pbl_decode_index_count(const pbl_layer* layer, void* eptr_out, void* stream);
+PBL_API int pbl_decode_index_fill(const pbl_layer* layer, const void* eptr, void* dsign_out, void* ent_out, void* stream);
+/* Borrow the three device buffers (16 B aligned); NULLs detach. */
+PBL_API int pbl_layer_attach_decode_index(pbl_layer* layer, const void* dsign, const void* eptr, const void* ent);
+
+/* pbl_linear_forward with a caller-owned device workspace for the decode kernel's cross-CTA reduction:
+ * >= pbl_decode_workspace_bytes(layer, M) bytes, 16 B aligned, ZERO-INITIALISED ONCE by the caller (the kernel
+ * leaves its arrival counters at zero), used by one stream at a time; it may be shared by all layers of a
+ * device.  Calls that do not take the decode kernel ignore it.  Without a workspace (pbl_linear_forward) the
+ * decode kernel takes a transient one from the stream-ordered pool and zeroes its counters on every call. */
+PBL_API size_t pbl_decode_workspace_bytes(const pbl_layer* layer, int64_t M);
+PBL_API int pbl_linear_forward_ws(const pbl_layer* layer, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
 /* XNOR-popcount forward of BiRealLinear (quant/quantizer.py:151-169): activations are binarized too,
  *   y[m][i] = sum_j sign(x[m][j]) * w_sim[i][j]        (fp32 out, NO bias -- the reference drops it, :168)
  * evaluated as hi*(popc(b&xp)-popc(b&xn)) + lo*(popc(nb&xp)-popc(nb&xn)) over the packed sign plane.
@@ -152,8 +178,8 @@ PBL_API int pbl_bireal_forward(const pbl_layer* layer, const void* x, int64_t ld
 
 /* Which kernel pbl_linear_forward would launch for this (layer, M): 0 = CUDA-core bit-plane
  * kernel (fp32 I/O), 1 = tcgen05 bit-plane GEMM (M above PBL_SKINNY_MAX_M, default 16),
- * 2 = mma.sync bit-plane skinny kernel (decode), 3 = tcgen05 split-K cluster kernel (M <= 128).
- * PBL_FORCE_KERNEL=0|1|2|3 overrides (tests). */
+ * 2 = mma.sync bit-plane skinny kernel (decode without a decode index), 3 = tcgen05 split-K cluster kernel
+ * (M <= 128), 4 = decode kernel (M <= 16, decode index attached).  PBL_FORCE_KERNEL=0|1|2|3|4 overrides (tests). */
 PBL_API int pbl_select_kernel(const pbl_layer* layer, int64_t M);
 
 /* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */

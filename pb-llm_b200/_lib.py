@@ -23,6 +23,10 @@ class PblLayerDesc(C.Structure):
                 ("affine", C.c_void_p), ("bias", C.c_void_p), ("sign_planes", C.c_void_p)]
 
 
+class PblDecodeSizes(C.Structure):
+    _fields_ = [("blocks", C.c_int64), ("dsign_bytes", C.c_size_t), ("eptr_bytes", C.c_size_t)]
+
+
 # name -> (restype, argtypes): every symbol include/pbllm.h declares
 SYMBOLS = {
     "pbl_pack_sizes": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(PblSizes)]),
@@ -37,6 +41,13 @@ SYMBOLS = {
     "pbl_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pbl_linear_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
                                      C.c_void_p]),
+    "pbl_linear_forward_ws": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+                                        C.c_void_p, C.c_size_t, C.c_void_p]),
+    "pbl_decode_index_sizes": (C.c_int, [C.c_void_p, C.POINTER(PblDecodeSizes)]),
+    "pbl_decode_index_count": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pbl_decode_index_fill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pbl_layer_attach_decode_index": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pbl_decode_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64]),
     "pbl_forward_host_workspace": (C.c_size_t, [C.c_void_p, C.c_int64]),
     "pbl_linear_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pbl_bireal_workspace": (C.c_size_t, [C.c_void_p, C.c_int64]),
@@ -76,7 +87,7 @@ def load():
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.pbl_abi_version() != 2:
+    if lib.pbl_abi_version() != 3:
         raise RuntimeError("libpbllm.so ABI version mismatch")
     _lib = lib
     return lib

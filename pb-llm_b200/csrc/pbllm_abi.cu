@@ -157,6 +157,7 @@ int pbl_layer_create(const pbl_layer_desc* d, pbl_layer** out) {
     L->planes = (const uint4*)d->planes; L->vptr = (const uint32_t*)d->vptr; L->vals = d->vals;
     L->affine = (const float2*)d->affine; L->bias = (const float*)d->bias;
     L->sign_planes = (const uint2*)d->sign_planes;
+    L->dsign = nullptr; L->eptr = nullptr; L->ent = nullptr;
     *out = reinterpret_cast<pbl_layer*>(L);
     return PBL_OK;
 }
@@ -191,7 +192,7 @@ static int splitk_max_m() {   // M up to which the split-K cluster kernel is pre
 }
 
 // 0 = CUDA-core bit-plane kernel, 1 = tcgen05 GEMM (single-CTA / CTA-pair), 2 = mma.sync skinny kernel,
-// 3 = tcgen05 split-K cluster kernel (M <= 128); -1 = forced kernel unsupported
+// 3 = tcgen05 split-K cluster kernel (M <= 128), 4 = decode kernel (decode index attached); -1 = forced kernel unsupported
 static int select_impl(const Layer& L, const void* x, int64_t ldx, const void* y, int64_t ldy, int64_t M) {
     const bool tc_ok = gemm_tc_supported(L, x, ldx, y, ldy, M);
     const bool sk_ok = skinny_supported(L, M);
@@ -201,7 +202,9 @@ static int select_impl(const Layer& L, const void* x, int64_t ldx, const void* y
     if (f == 1) return tc_ok ? 1 : -1;
     if (f == 2) return sk_ok ? 2 : -1;
     if (f == 3) return ck_ok ? 3 : -1;
+    if (f == 4) return decode_supported(L, ldx, M) ? 4 : -1;
     if (!sk_ok) return 0;                       // fp32 I/O: CUDA cores
+    if (M <= skinny_max_m() && decode_supported(L, ldx, M)) return 4;   // decode: positioned-entry kernel, stream-K over warps
     if (M <= skinny_max_m()) return 2;          // decode: mma.sync skinny kernel (measured faster than split-K up to 16 tokens)
     if (ck_ok && M <= splitk_max_m()) return 3; // short prompts: split-K cluster kernel (2x the single-CTA GEMM at M = 64)
     if (!tc_ok) return 2;
@@ -216,6 +219,11 @@ int pbl_select_kernel(const pbl_layer* layer, int64_t M) {
 
 int pbl_linear_forward(const pbl_layer* layer, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M,
                        void* stream) {
+    return pbl_linear_forward_ws(layer, x, ldx, y, ldy, M, nullptr, 0, stream);
+}
+
+int pbl_linear_forward_ws(const pbl_layer* layer, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M,
+                          void* workspace, size_t workspace_bytes, void* stream) {
     if (!layer) { set_error("pbl_linear_forward: null layer"); return PBL_ERR_NULL; }
     const Layer& L = *reinterpret_cast<const Layer*>(layer);
     if (M < 0) { set_error("pbl_linear_forward: M=%lld < 0", (long long)M); return PBL_ERR_SHAPE; }
@@ -233,7 +241,53 @@ int pbl_linear_forward(const pbl_layer* layer, const void* x, int64_t ldx, void*
     if (k == 1) return launch_gemm_tc(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
     if (k == 2) return launch_skinny(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
     if (k == 3) return launch_gemm_splitk(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
+    if (k == 4) return launch_decode(L, x, ldx, y, ldy, M, workspace, workspace_bytes, (cudaStream_t)stream);
     return launch_gemv(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
+}
+
+int pbl_decode_index_sizes(const pbl_layer* layer, pbl_decode_sizes* out) {
+    if (!layer || !out) { set_error("pbl_decode_index_sizes: null pointer"); return PBL_ERR_NULL; }
+    const Layer& L = *reinterpret_cast<const Layer*>(layer);
+    if (L.dtype != PBL_F16 && L.dtype != PBL_BF16) { set_error("the decode index needs an fp16 / bf16 layer"); return PBL_ERR_DTYPE; }
+    out->blocks = L.tiles_r * kRgPerTile * L.tiles_c;
+    out->dsign_bytes = (size_t)out->blocks * kRgRows * sizeof(uint2);
+    out->eptr_bytes = (size_t)(out->blocks + 1) * sizeof(uint32_t);
+    return PBL_OK;
+}
+
+int pbl_decode_index_count(const pbl_layer* layer, void* eptr_out, void* stream) {
+    if (!layer || !eptr_out) { set_error("pbl_decode_index_count: null pointer"); return PBL_ERR_NULL; }
+    const Layer& L = *reinterpret_cast<const Layer*>(layer);
+    if (L.dtype != PBL_F16 && L.dtype != PBL_BF16) { set_error("the decode index needs an fp16 / bf16 layer"); return PBL_ERR_DTYPE; }
+    int rc = device_check_impl();
+    if (rc) return rc;
+    return launch_decode_index_count(L, (uint32_t*)eptr_out, (cudaStream_t)stream);
+}
+
+int pbl_decode_index_fill(const pbl_layer* layer, const void* eptr, void* dsign_out, void* ent_out, void* stream) {
+    if (!layer || !eptr || !dsign_out || !ent_out) { set_error("pbl_decode_index_fill: null pointer"); return PBL_ERR_NULL; }
+    const Layer& L = *reinterpret_cast<const Layer*>(layer);
+    if (L.dtype != PBL_F16 && L.dtype != PBL_BF16) { set_error("the decode index needs an fp16 / bf16 layer"); return PBL_ERR_DTYPE; }
+    if (!aligned16(dsign_out) || !aligned16(ent_out)) { set_error("pbl_decode_index_fill: dsign/ent must be 16 B aligned"); return PBL_ERR_ALIGN; }
+    int rc = device_check_impl();
+    if (rc) return rc;
+    return launch_decode_index_fill(L, (const uint32_t*)eptr, (uint2*)dsign_out, (uint32_t*)ent_out, (cudaStream_t)stream);
+}
+
+int pbl_layer_attach_decode_index(pbl_layer* layer, const void* dsign, const void* eptr, const void* ent) {
+    if (!layer) { set_error("pbl_layer_attach_decode_index: null layer"); return PBL_ERR_NULL; }
+    Layer& L = *reinterpret_cast<Layer*>(layer);
+    if (!dsign && !eptr && !ent) { L.dsign = nullptr; L.eptr = nullptr; L.ent = nullptr; return PBL_OK; }
+    if (!dsign || !eptr || !ent) { set_error("pbl_layer_attach_decode_index: all three buffers or none"); return PBL_ERR_NULL; }
+    if (L.dtype != PBL_F16 && L.dtype != PBL_BF16) { set_error("the decode index needs an fp16 / bf16 layer"); return PBL_ERR_DTYPE; }
+    if (!aligned16(dsign) || !aligned16(ent)) { set_error("pbl_layer_attach_decode_index: dsign/ent must be 16 B aligned"); return PBL_ERR_ALIGN; }
+    L.dsign = (const uint2*)dsign; L.eptr = (const uint32_t*)eptr; L.ent = (const uint32_t*)ent;
+    return PBL_OK;
+}
+
+size_t pbl_decode_workspace_bytes(const pbl_layer* layer, int64_t M) {
+    if (!layer || M <= 0) return 0;
+    return decode_workspace_bytes(*reinterpret_cast<const Layer*>(layer), M);
 }
 
 size_t pbl_bireal_workspace(const pbl_layer* layer, int64_t M) {

@@ -26,6 +26,10 @@ struct Layer {  // the opaque pbl_layer
     const float2* affine; // [n_pad][groups] {lo, hi}
     const float* bias;
     const uint2* sign_planes;  // optional compact sign-only planes (nnz == 0 layers)
+    // optional decode index (pbl_decode_index_*): row-group-major sign words, entry offsets, positioned salient entries
+    const uint2* dsign;
+    const uint32_t* eptr;
+    const uint32_t* ent;
 };
 
 void set_error(const char* fmt, ...);
@@ -66,6 +70,12 @@ int launch_gemm_tc(const Layer& L, const void* x, int64_t ldx, void* y, int64_t 
 bool gemm_tc_supported(const Layer& L, const void* x, int64_t ldx, const void* y, int64_t ldy, int64_t M);
 int launch_skinny(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s);
 bool skinny_supported(const Layer& L, int64_t M);
+int launch_decode_index_count(const Layer& L, uint32_t* eptr, cudaStream_t s);
+int launch_decode_index_fill(const Layer& L, const uint32_t* eptr, uint2* dsign, uint32_t* ent, cudaStream_t s);
+bool decode_supported(const Layer& L, int64_t ldx, int64_t M);
+size_t decode_workspace_bytes(const Layer& L, int64_t M);
+int launch_decode(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws, size_t ws_bytes,
+                  cudaStream_t s);
 size_t bireal_workspace_bytes(const Layer& L, int64_t M);
 int launch_bireal(const Layer& L, const void* x, int64_t ldx, int x_dtype, float* y, int64_t ldy, int64_t M, void* workspace,
                   cudaStream_t s);

@@ -1,0 +1,588 @@
+// Decode kernel (M <= 16 tokens per call, fp16 / bf16): the HBM-bound regime of the bit-plane forward.
+//
+// Same math as every other kernel of the library (y = x . w_sim^T + b, the EXACT w_sim tile rebuilt in shared
+// memory and multiplied on the tensor cores with fp32 accumulation), reorganised around what bounds a
+// 2-microsecond kernel: instructions per weight, dependent DRAM round trips, and SM load balance.
+//
+//  * decode index (built once at pack time, pbl_decode_index_*): the layer in ROW-GROUP-MAJOR block order --
+//    block (rg, kb) = 32 output rows x 64 input columns, linear id rg*tiles_c + kb:
+//      dsign uint2 [blocks][32]        the sign words of the block's rows (1 bit / weight)
+//      eptr  u32   [blocks + 1]        offset of each block's salient entries, in 16-byte units
+//      ent   u32   [..]                one entry per salient weight: (byte offset in the 4 KB swizzled tile) << 16
+//                                      | the value's 16 bits; blocks padded to 4 entries with copies of their last
+//                                      entry (an idempotent store).
+//    With explicit positions the salient patch is lane-balanced: entry e of a block is handled by lane e/4 % 32,
+//    3 instructions per entry, no per-row bit walking, no warp scan, no divergence.
+//  * warp-granular stream-K: the blocks of the layer are dealt out in contiguous, equal (+-1) runs to the
+//    warps of a fixed grid (2 CTAs per SM), so every SM gets the same number of blocks whatever N and K are.
+//    A warp's run covers at most two partial row groups (head / tail) plus whole ones; partials are reduced
+//    across the warps of the CTA in shared memory, and across CTAs through a small global workspace with one
+//    arrival counter per row group -- slots are summed in CTA order by the last arriver, so the result is
+//    deterministic.
+//  * every weight-side load of a warp's first blocks is issued before griddepcontrol.wait: under programmatic
+//    dependent launch the packed stream of layer i+1 is in flight while layer i still computes.
+#include <cstdlib>
+#include <type_traits>
+
+#include "pbllm_tc_ptx.cuh"
+
+namespace pbl {
+
+namespace dk {
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kTok = 8;                       // tokens per pass (mma N)
+constexpr int kTileBytes = kRgRows * kTileCols * 2;   // 4096: the warp's 32x64 16-bit weight tile (128B rows, swizzled)
+constexpr int kXBytes = kTok * kTileCols * 2;         // 1024: the block's activations, 8 token rows of 128 B, swizzled
+constexpr int kHeadBytes = kRgRows * kTok * 4;        // 1024: the warp's head-segment partial (fp32 [8 tokens][32 rows])
+constexpr int kWarpBytes = kTileBytes + kXBytes + kHeadBytes;   // 6144
+constexpr int kOut = kRgRows * kTok;          // 256 outputs per (row group, token pass) == kThreads
+static_assert(kOut == kThreads, "one thread per output in the cross-warp reduction");
+constexpr uint32_t kCntCap = 16384;           // arrival counters at the head of the workspace (u32 each)
+
+struct Params {
+    const uint2* dsign;
+    const uint32_t* eptr;
+    const uint4* ent;
+    const float2* affine;
+    const float* bias;
+    const void* x;
+    void* y;
+    int64_t ldx, ldy;
+    float* ws_part;       // [token pass][row group][slots][256] fp32 partials
+    uint32_t* ws_cnt;     // [token pass][row group] arrival counters, zero between kernels
+    int M, N, K;
+    uint32_t tiles_c, groups, tiles_per_group;
+    uint32_t nblocks;     // row groups * tiles_c
+    uint32_t rgs;
+    uint32_t slots;       // partial slots per row group
+};
+}  // namespace dk
+
+template <typename T>
+__device__ __forceinline__ void dk_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                       uint32_t b1) {
+    if constexpr (std::is_same<T, __half>::value) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    } else {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+}
+
+__device__ __forceinline__ void dk_ldsm4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr)
+                 : "memory");
+}
+
+// 64 sign bits of one weight row -> 64 exact {lo,hi} 16-bit values, written as 8 swizzled 16 B chunks (chunk c holds
+// columns 8c..8c+7 at row + ((c ^ (row & 7)) << 4); `brow` already carries (row & 7) << 4, so that is brow ^ (c << 4)):
+// the same PRMT byte-sign replicate + LOP3 select as expand_row.
+__device__ __forceinline__ void dk_expand_dense(const uint2 sg, const uint32_t LL, const uint32_t DD, const uint32_t brow) {
+#pragma unroll
+    for (int wd = 0; wd < 2; ++wd) {
+        const uint32_t s = wd ? sg.y : sg.x;
+        const uint32_t X0 = s, X1 = s << 1, X2 = s << 2, X3 = s << 3, X4 = s << 4, X5 = s << 5, X6 = s << 6, X7 = s << 7;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t sel = 0x8888u | (uint32_t)c | ((uint32_t)c << 4) | ((uint32_t)(4 + c) << 8) | ((uint32_t)(4 + c) << 12);
+            const uint32_t h0 = sel_xor_and(LL, DD, prmt(X7, X6, sel));
+            const uint32_t h1 = sel_xor_and(LL, DD, prmt(X5, X4, sel));
+            const uint32_t h2 = sel_xor_and(LL, DD, prmt(X3, X2, sel));
+            const uint32_t h3 = sel_xor_and(LL, DD, prmt(X1, X0, sel));
+            sts_v4(brow ^ ((uint32_t)(wd * 4 + c) << 4), h0, h1, h2, h3);
+        }
+    }
+}
+
+// four salient entries: store each value's 16 bits at its (pre-swizzled) byte offset in the tile
+__device__ __forceinline__ void dk_patch4(const uint32_t tile_s, const uint4 e) {
+    sts_u16(tile_s + (e.x >> 16), (uint16_t)e.x);
+    sts_u16(tile_s + (e.y >> 16), (uint16_t)e.y);
+    sts_u16(tile_s + (e.z >> 16), (uint16_t)e.z);
+    sts_u16(tile_s + (e.w >> 16), (uint16_t)e.w);
+}
+
+// kOcc = CTAs per SM the register budget is sized for: 3 -> 85 registers (no spills), 4 -> 64 (one spilled word)
+template <typename T, int kOcc>
+__global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk::Params p) {
+    using namespace dk;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint32_t s_wlo[kWarps], s_whi[kWarps];
+    __shared__ uint32_t s_fix[3];                 // {slot, expected, last}
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    uint8_t* wsm = smem + wid * kWarpBytes;
+    const uint32_t tile_s = smem_u32(wsm);
+    const uint32_t xs_s = tile_s + kTileBytes;
+    float* head_red = reinterpret_cast<float*>(wsm + kTileBytes + kXBytes);
+    float* tail_red = reinterpret_cast<float*>(wsm);      // aliases the tile: written only after the warp's last block
+    uint32_t* eptr_s = reinterpret_cast<uint32_t*>(smem + kWarps * kWarpBytes);
+
+    const uint32_t B = p.nblocks, G = gridDim.x, TC = p.tiles_c;
+    const uint32_t c_lo = (uint32_t)(((uint64_t)blockIdx.x * B) / G), c_hi = (uint32_t)(((uint64_t)(blockIdx.x + 1) * B) / G);
+    uint32_t w_lo, w_hi;
+    {
+        uint32_t v = 0;
+        if (lane < 2) v = (uint32_t)(((uint64_t)(blockIdx.x * kWarps + wid + lane) * B) / ((uint64_t)G * kWarps));
+        w_lo = __shfl_sync(0xffffffffu, v, 0);
+        w_hi = __shfl_sync(0xffffffffu, v, 1);
+    }
+    const int m0 = blockIdx.y * kTok;
+
+    // Programmatic dependent launch: the next kernel in the stream may start its own weight prefetch now; everything
+    // below up to griddepcontrol.wait touches only immutable packed weights.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    if (lane == 0) { s_wlo[wid] = w_lo; s_whi[wid] = w_hi; }
+    for (uint32_t i = tid; i <= c_hi - c_lo; i += kThreads) eptr_s[i] = __ldg(p.eptr + c_lo + i);
+    const uint2* sgp = p.dsign + (size_t)w_lo * kRgRows + lane;
+    uint2 sg = make_uint2(0, 0);
+    if (w_lo < w_hi) sg = __ldg(sgp);
+    __syncthreads();
+
+    uint32_t rg = 0, kb = 0;
+    if (w_lo < w_hi) { rg = w_lo / TC; kb = w_lo - rg * TC; }
+    const uint32_t rg_first = rg;
+    const bool grouped = p.groups > 1;
+    uint32_t cur_g = grouped ? kb / p.tiles_per_group : 0u;
+    const uint32_t* ep = eptr_s + (w_lo - c_lo);    // eptr of the current block
+    uint32_t eb = 0, n4 = 0;
+    uint4 ea = make_uint4(0, 0, 0, 0), ec = make_uint4(0, 0, 0, 0);
+    float2 af = make_float2(0.f, 0.f);
+    if (w_lo < w_hi) {
+        eb = ep[0];
+        n4 = ep[1] - eb;
+        const uint4* e = p.ent + (eb + lane);
+        if (lane < n4) ea = __ldg(e);
+        if (lane + 32u < n4) ec = __ldg(e + 32);
+        af = __ldg(p.affine + (size_t)(rg * kRgRows + lane) * p.groups + cur_g);
+    }
+    uint32_t LL, DD;
+    {
+        const uint32_t lo = bits16<T>(af.x), hi = bits16<T>(af.y);
+        LL = lo | (lo << 16);
+        DD = (lo ^ hi) * 0x10001u;
+    }
+
+    // ---- activation loads: lane -> (token = lane>>2, 16-column segment = lane&3) of the 8 x 64 block ----------
+    const uint32_t xtok = lane >> 2, xseg = lane & 3u;
+    const bool x_fast = ((p.ldx & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15u) == 0) && ((p.K & 63) == 0);
+    const bool x_tok_ok = (m0 + (int)xtok) < p.M;
+    // byte offset of (my token row, my 16-column segment, k-block 0); 32-bit (checked by the launcher) and opaque to the
+    // compiler so it stays in a register instead of being recomputed every block
+    uint32_t xoff_row = (uint32_t)(((int64_t)(m0 + (x_tok_ok ? (int)xtok : 0)) * p.ldx + 16 * xseg) * 2);
+    asm volatile("" : "+r"(xoff_row));
+    uint32_t xoff = xoff_row + kb * (kTileCols * 2u);          // loop-carried: advances one k-block per iteration
+    const uint8_t* xbytes = reinterpret_cast<const uint8_t*>(p.x);
+    // fast path (x_fast: 16 B aligned rows, K a multiple of 64): two unconditional 16 B loads -- rows past M read token
+    // m0's row, whose products land in output columns that are never stored.  Anything else: bounds-checked elements.
+    auto load_x = [&](uint32_t kblk, uint4& xa, uint4& xb) {
+        if (x_fast) {
+            const uint4* p4 = reinterpret_cast<const uint4*>(xbytes + xoff);
+            xa = __ldg(p4);
+            xb = __ldg(p4 + 1);
+        } else {
+            const uint16_t* q = reinterpret_cast<const uint16_t*>(xbytes + xoff);
+            const int col = (int)(kblk * kTileCols + 16 * xseg);
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int cc = col + 2 * i;
+                uint32_t v = 0;
+                if (x_tok_ok && cc < p.K) v = (uint32_t)q[2 * i];
+                if (x_tok_ok && cc + 1 < p.K) v |= (uint32_t)q[2 * i + 1] << 16;
+                w[i] = v;
+            }
+            xa = make_uint4(w[0], w[1], w[2], w[3]);
+            xb = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+    };
+
+    // shared-memory addresses of this lane
+    const uint32_t r7 = lane & 7u;
+    const uint32_t brow = (tile_s + lane * 128u) | (r7 << 4);                     // my weight row; chunk c lives at brow ^ (c << 4)
+    const uint32_t xst0 = xs_s + xtok * 128u + (((2u * xseg) ^ xtok) << 4);       // my two 16 B activation chunks
+    const uint32_t lm_row = (lane & 7u) + ((lane >> 3) & 1u) * 8u;                // A fragments (weights)
+    const uint32_t lm_base0 = tile_s + lm_row * 128u + (((lane >> 4) ^ (lm_row & 7u)) << 4);
+    const uint32_t xl_base = xs_s + r7 * 128u + (((lane >> 3) ^ r7) << 4);        // B fragments (activations)
+    const uint32_t g4 = lane >> 2, t4 = lane & 3u;
+    uint32_t lm_q[4];                                                             // ldmatrix row address per k16 step
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        lm_q[q] = lm_base0 ^ ((uint32_t)q << 5);
+        asm volatile("" : "+r"(lm_q[q]));                                         // keep in a register (no rematerialisation)
+    }
+    uint32_t xl0 = xl_base, xl1 = xl_base ^ 64u, brow_r = brow, xst_r = xst0;
+    asm volatile("" : "+r"(xl0), "+r"(xl1), "+r"(brow_r), "+r"(xst_r));
+
+    float acc[2][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[0][i] = acc[1][i] = 0.f;
+
+    // fp32 [token][row] layout of one row group's outputs: index m*32 + r
+    auto store_frag = [&](float* dst) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t r = 16u * h + g4;
+            dst[(2u * t4) * kRgRows + r] = acc[h][0];
+            dst[(2u * t4 + 1u) * kRgRows + r] = acc[h][1];
+            dst[(2u * t4) * kRgRows + r + 8u] = acc[h][2];
+            dst[(2u * t4 + 1u) * kRgRows + r + 8u] = acc[h][3];
+        }
+    };
+
+    // activations (and y, and the workspace) belong to the stream's earlier kernels: wait before the first touch
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    uint4 xa = make_uint4(0, 0, 0, 0), xb = make_uint4(0, 0, 0, 0);
+    if (w_lo < w_hi) load_x(kb, xa, xb);
+
+    // Every stream is prefetched IN PLACE: a register set is reloaded for the next block right after its last use,
+    // which gives each load about one block of cover without a second register set or rotation moves.
+    for (uint32_t blk = w_lo; blk < w_hi; ++blk) {
+        const bool more = blk + 1 < w_hi;
+        if (grouped) {
+            const uint32_t g = kb / p.tiles_per_group;
+            if (g != cur_g) {
+                cur_g = g;
+                af = __ldg(p.affine + (size_t)(rg * kRgRows + lane) * p.groups + g);
+                const uint32_t lo = bits16<T>(af.x), hi = bits16<T>(af.y);
+                LL = lo | (lo << 16);
+                DD = (lo ^ hi) * 0x10001u;
+            }
+        }
+
+        __syncwarp();                                   // the previous block's ldmatrix reads are done
+        dk_expand_dense(sg, LL, DD, brow_r);
+        if (more) { sgp += kRgRows; sg = __ldg(sgp); }
+        __syncwarp();                                   // dense rows land before other lanes patch them
+        if (lane < n4) dk_patch4(tile_s, ea);
+        if (lane + 32u < n4) dk_patch4(tile_s, ec);
+        for (uint32_t i = 64u + lane; i < n4; i += 32u) dk_patch4(tile_s, __ldg(p.ent + (eb + i)));   // rare: > 256 salient in a block
+        if (more) {
+            ++ep;
+            eb = ep[0];
+            n4 = ep[1] - eb;
+            const uint4* e = p.ent + (eb + lane);
+            asm volatile("" : "+l"(e));                 // one address computation for both predicated loads
+            if (lane < n4) ea = __ldg(e);
+            if (lane + 32u < n4) ec = __ldg(e + 32);
+        }
+        sts_v4(xst_r, xa.x, xa.y, xa.z, xa.w);
+        sts_v4(xst_r ^ 16u, xb.x, xb.y, xb.z, xb.w);
+        ++kb;
+        const bool rg_end = kb == TC;
+        xoff = rg_end ? xoff_row : xoff + kTileCols * 2u;
+        if (more) load_x(rg_end ? 0u : kb, xa, xb);
+        __syncwarp();                                   // tile and activations visible to the whole warp
+
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            uint32_t b[4];
+            dk_ldsm4(jj ? xl1 : xl0, b[0], b[1], b[2], b[3]);
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq) {
+                const uint32_t q = 2u * jj + qq;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t a0, a1, a2, a3;
+                    dk_ldsm4(lm_q[q] + (uint32_t)h * 2048u, a0, a1, a2, a3);
+                    dk_mma<T>(acc[h], a0, a1, a2, a3, b[2 * qq], b[2 * qq + 1]);
+                }
+            }
+        }
+
+        // ---- end of this warp's part of the row group? -----------------------------------------------------
+        if (rg_end || !more) {
+            const bool whole = rg_end && (w_lo <= rg * TC);      // this warp saw every k-block of the row group
+            if (whole) {                                         // finish it here: + bias, round, store
+                __syncwarp();
+                store_frag(tail_red);
+                __syncwarp();
+                const int orow = (int)(rg * kRgRows + lane);
+                if (orow < p.N) {
+                    const float bv = p.bias ? p.bias[orow] : 0.f;
+#pragma unroll
+                    for (int m = 0; m < kTok; ++m)
+                        if (m0 + m < p.M)
+                            reinterpret_cast<T*>(p.y)[(int64_t)(m0 + m) * p.ldy + orow] = from_f32<T>(bv + tail_red[m * kRgRows + lane]);
+                }
+            } else if (rg == rg_first) {
+                store_frag(head_red);                            // head partial: its own buffer, the warp may go on
+            } else {
+                __syncwarp();
+                store_frag(tail_red);                            // tail partial: last thing this warp does
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[0][i] = acc[1][i] = 0.f;
+            if (rg_end) {
+                kb = 0;
+                ++rg;
+                if (more) {
+                    cur_g = 0;
+                    af = __ldg(p.affine + (size_t)(rg * kRgRows + lane) * p.groups);
+                    const uint32_t lo = bits16<T>(af.x), hi = bits16<T>(af.y);
+                    LL = lo | (lo << 16);
+                    DD = (lo ^ hi) * 0x10001u;
+                }
+            }
+        }
+    }
+
+    // ---- cross-warp, then cross-CTA reduction of the partial row groups -------------------------------------------
+    __syncthreads();
+    if (c_lo >= c_hi) return;
+    const uint32_t rg_a = c_lo / TC, rg_b = (c_hi - 1) / TC;
+    const uint32_t om = tid >> 5, orr = tid & 31u;          // this thread's output: token om, row orr of the row group
+    for (uint32_t r = rg_a; r <= rg_b; ++r) {
+        const uint32_t r_lo = r * TC, r_hi = r_lo + TC;
+        const uint32_t seg_lo = max(c_lo, r_lo), seg_hi = min(c_hi, r_hi);
+        float v = 0.f;
+        uint32_t contributors = 0;
+        bool single_whole = false;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t wl = s_wlo[w], wh = s_whi[w];
+            if (wl < wh && wl < seg_hi && wh > seg_lo) {
+                ++contributors;
+                if (wl <= r_lo && wh >= r_hi) { single_whole = true; continue; }   // that warp stored the row group itself
+                const float* src = reinterpret_cast<const float*>(smem + w * kWarpBytes + ((wl / TC == r) ? (kTileBytes + kXBytes) : 0));
+                v += src[tid];
+            }
+        }
+        if (single_whole || contributors == 0) continue;
+        const int orow = (int)(r * kRgRows + orr);
+        const bool ok = (orow < p.N) && (m0 + (int)om < p.M);
+        if (seg_lo == r_lo && seg_hi == r_hi) {              // the whole row group lives in this CTA
+            if (ok) reinterpret_cast<T*>(p.y)[(int64_t)(m0 + om) * p.ldy + orow] = from_f32<T>((p.bias ? p.bias[orow] : 0.f) + v);
+            continue;
+        }
+        // split across CTAs: park the partial in this CTA's slot, the last arriver sums the slots in CTA order
+        if (tid == 0) {
+            const uint32_t first = (uint32_t)((((uint64_t)r_lo + 1) * G - 1) / B);      // CTA owning block r_lo
+            const uint32_t lastc = (uint32_t)((((uint64_t)r_hi) * G - 1) / B);          // CTA owning block r_hi - 1
+            s_fix[0] = blockIdx.x - first;
+            s_fix[1] = lastc - first + 1u;
+        }
+        __syncthreads();
+        const uint32_t slot = s_fix[0], expected = s_fix[1];
+        float* part = p.ws_part + (((size_t)blockIdx.y * p.rgs + r) * p.slots) * kOut;
+        uint32_t* cnt = p.ws_cnt + (size_t)blockIdx.y * p.rgs + r;
+        part[(size_t)slot * kOut + tid] = v;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_fix[2] = (atomicAdd(cnt, 1u) + 1u == expected) ? 1u : 0u;
+        __syncthreads();
+        if (s_fix[2]) {
+            __threadfence();
+            float s = (p.bias && orow < p.N) ? p.bias[orow] : 0.f;
+            for (uint32_t k = 0; k < expected; ++k) s += __ldcg(part + (size_t)k * kOut + tid);
+            if (ok) reinterpret_cast<T*>(p.y)[(int64_t)(m0 + om) * p.ldy + orow] = from_f32<T>(s);
+            if (tid == 0) *cnt = 0u;                         // ready for the next kernel that uses this workspace
+        }
+        __syncthreads();                                     // s_fix is reused by the next row group
+    }
+}
+
+// ---- decode index construction (one-time, from the packed form) ---------------------------------------------------
+// pass 1: 16-byte units of salient entries per block, row-group-major order; scanned in place afterwards
+__global__ void decode_index_count_kernel(const uint32_t* __restrict__ vptr, uint32_t* __restrict__ eptr, uint32_t tiles_c,
+                                          uint32_t nblocks) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nblocks) return;
+    const uint32_t rg = i / tiles_c, kb = i - rg * tiles_c;
+    const uint32_t tr = rg / kRgPerTile, rgi = rg % kRgPerTile;
+    const size_t old = ((size_t)tr * tiles_c + kb) * kRgPerTile + rgi;
+    const uint32_t cnt = vptr[old + 1] - vptr[old];
+    eptr[i] = (cnt + 3u) / 4u;
+}
+
+// pass 2: sign words and entries. CTA = one 128x64 plane tile, warp = one 32-row group, lane = row.
+__global__ void __launch_bounds__(128) decode_index_fill_kernel(const uint4* __restrict__ planes, const uint32_t* __restrict__ vptr,
+                                                                const uint16_t* __restrict__ vals, const uint32_t* __restrict__ eptr,
+                                                                uint32_t tiles_c, uint2* __restrict__ dsign,
+                                                                uint32_t* __restrict__ ent) {
+    const uint32_t lane = threadIdx.x & 31u, rgi = threadIdx.x >> 5;
+    const size_t tile = blockIdx.x;
+    const uint32_t tr = (uint32_t)(tile / tiles_c), kb = (uint32_t)(tile % tiles_c);
+    const uint4 pw = planes[tile * kTileRows + rgi * kRgRows + lane];
+    const size_t blk = (size_t)(tr * kRgPerTile + rgi) * tiles_c + kb;
+    dsign[blk * kRgRows + lane] = make_uint2(pw.x, pw.y);
+    const size_t old = tile * kRgPerTile + rgi;
+    const uint32_t vbase = vptr[old], cnt = vptr[old + 1] - vbase;
+    if (cnt == 0) return;                                   // warp-uniform
+    const uint32_t mine = (uint32_t)(__popc(pw.z) + __popc(pw.w));
+    uint32_t off = warp_excl_scan(mine, lane);
+    uint32_t* dst = ent + (size_t)eptr[blk] * 4u;
+    const bool owns_last = mine > 0 && off + mine == cnt;   // the last row with salient entries also writes the padding
+    uint32_t e = 0;
+#pragma unroll
+    for (int wd = 0; wd < 2; ++wd) {
+        uint32_t m = wd ? pw.w : pw.z;
+        while (m) {
+            const uint32_t col = (uint32_t)(__ffs(m) - 1) + 32u * wd;
+            m &= m - 1u;
+            const uint32_t pos = lane * 128u + ((((col >> 3) ^ (lane & 7u))) << 4) + (col & 7u) * 2u;   // byte offset in the swizzled tile
+            e = (pos << 16) | (uint32_t)vals[vbase + off];
+            dst[off++] = e;
+        }
+    }
+    if (owns_last)
+        for (uint32_t k = cnt; k < ((cnt + 3u) & ~3u); ++k) dst[k] = e;
+}
+
+void launch_scan_counts(uint32_t* v, int64_t n, cudaStream_t s);   // pbllm_pack.cu
+
+int launch_decode_index_count(const Layer& L, uint32_t* eptr, cudaStream_t s) {
+    const uint32_t nblocks = (uint32_t)(L.tiles_r * kRgPerTile * L.tiles_c);
+    decode_index_count_kernel<<<(nblocks + 255u) / 256u, 256, 0, s>>>(L.vptr, eptr, (uint32_t)L.tiles_c, nblocks);
+    int rc = check_cuda(cudaGetLastError(), "decode_index_count launch");
+    if (rc) return rc;
+    launch_scan_counts(eptr, nblocks, s);
+    count_launch(2);
+    return check_cuda(cudaGetLastError(), "decode_index scan launch");
+}
+
+int launch_decode_index_fill(const Layer& L, const uint32_t* eptr, uint2* dsign, uint32_t* ent, cudaStream_t s) {
+    decode_index_fill_kernel<<<(unsigned)(L.tiles_r * L.tiles_c), 128, 0, s>>>(L.planes, L.vptr, (const uint16_t*)L.vals, eptr,
+                                                                               (uint32_t)L.tiles_c, dsign, ent);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "decode_index_fill launch");
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------
+static int dk_ctas_per_sm() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PBL_DK_CTAS");
+        v = (e && *e) ? atoi(e) : 2;
+        if (v < 1) v = 1;
+        if (v > 4) v = 4;
+    }
+    return v;
+}
+
+static int dk_occupancy() {      // which register budget / launch-bounds variant to launch
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PBL_DK_OCC");
+        v = (e && *e) ? atoi(e) : 3;
+        if (v != 4) v = 3;
+    }
+    return v;
+}
+
+static int dk_num_sms() {
+    static int sms[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    return sms[dev] > 0 ? sms[dev] : 148;
+}
+
+struct DecodeGeom { uint32_t nblocks, rgs, grid, slots, passes; size_t ws_bytes; };
+
+static DecodeGeom decode_geom(const Layer& L, int64_t M) {
+    DecodeGeom g;
+    g.rgs = (uint32_t)(L.tiles_r * kRgPerTile);
+    g.nblocks = g.rgs * (uint32_t)L.tiles_c;
+    const uint32_t want = (uint32_t)(dk_num_sms() * dk_ctas_per_sm());
+    g.grid = g.nblocks < want ? g.nblocks : want;
+    g.slots = (uint32_t)(((uint64_t)L.tiles_c * g.grid + g.nblocks - 1) / g.nblocks) + 1u;
+    g.passes = (uint32_t)((M + dk::kTok - 1) / dk::kTok);
+    g.ws_bytes = (size_t)dk::kCntCap * 4u + (size_t)g.passes * g.rgs * g.slots * dk::kOut * 4u;
+    return g;
+}
+
+bool decode_supported(const Layer& L, int64_t ldx, int64_t M) {
+    if (!L.dsign || !L.eptr || !L.ent) return false;
+    if (L.dtype != PBL_F16 && L.dtype != PBL_BF16) return false;
+    if (M <= 0 || M > 64) return false;
+    if (ldx <= 0 || (uint64_t)M * (uint64_t)ldx * 2u >= (1ull << 31)) return false;   // 32-bit activation offsets
+    const DecodeGeom g = decode_geom(L, M);
+    return (uint64_t)g.passes * g.rgs <= dk::kCntCap;
+}
+
+size_t decode_workspace_bytes(const Layer& L, int64_t M) {
+    if (!decode_supported(L, L.K, M)) return 0;
+    return decode_geom(L, M).ws_bytes;
+}
+
+template <typename T, int kOcc>
+static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws, cudaStream_t s) {
+    const DecodeGeom g = decode_geom(L, M);
+    const uint32_t max_run = (g.nblocks + g.grid - 1) / g.grid + 1u;               // blocks in a CTA's run (upper bound)
+    const int smem = dk::kWarps * dk::kWarpBytes + (int)(((max_run + 2u) * 4u + 15u) & ~15u);
+    if (smem > 200 * 1024) { set_error("decode kernel: layer too large for the eptr staging area"); return PBL_ERR_UNSUPPORTED; }
+    static int attr_smem_dev[64] = {};   // function attributes are per device
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (cur_dev < 0 || cur_dev >= 64) cur_dev = 0;
+    if (attr_smem_dev[cur_dev] < smem) {
+        int rc = check_cuda(cudaFuncSetAttribute(decode_mma_kernel<T, kOcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                            "cudaFuncSetAttribute(decode smem)");
+        if (rc) return rc;
+        attr_smem_dev[cur_dev] = smem;
+    }
+    dk::Params p;
+    p.dsign = L.dsign; p.eptr = L.eptr; p.ent = reinterpret_cast<const uint4*>(L.ent);
+    p.affine = L.affine; p.bias = L.bias; p.x = x; p.y = y; p.ldx = ldx; p.ldy = ldy;
+    p.ws_cnt = reinterpret_cast<uint32_t*>(ws);
+    p.ws_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + (size_t)dk::kCntCap * 4u);
+    p.M = (int)M; p.N = (int)L.N; p.K = (int)L.K;
+    p.tiles_c = (uint32_t)L.tiles_c; p.groups = (uint32_t)L.groups; p.tiles_per_group = (uint32_t)L.tiles_per_group;
+    p.nblocks = g.nblocks; p.rgs = g.rgs; p.slots = g.slots;
+
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g.grid, g.passes);
+    cfg.blockDim = dim3(dk::kThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static int pdl = -1;
+    if (pdl < 0) { const char* e = getenv("PBL_PDL"); pdl = (e && *e) ? atoi(e) : 1; }
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, decode_mma_kernel<T, kOcc>, p);
+    count_launch();
+    return check_cuda(le, "decode launch");
+}
+
+// ws == nullptr: take a transient workspace from the stream-ordered pool and zero its counters (slower: the memset
+// sits between consecutive decode kernels); callers on the hot path pass a persistent zero-initialised workspace.
+int launch_decode(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws, size_t ws_bytes,
+                  cudaStream_t s) {
+    const DecodeGeom g = decode_geom(L, M);
+    void* own = nullptr;
+    if (ws) {
+        if (ws_bytes < g.ws_bytes) { set_error("decode workspace too small: %zu < %zu bytes", ws_bytes, g.ws_bytes); return PBL_ERR_SHAPE; }
+        if (reinterpret_cast<uintptr_t>(ws) & 15u) { set_error("decode workspace must be 16 B aligned"); return PBL_ERR_ALIGN; }
+    } else {
+        int rc = check_cuda(cudaMallocAsync(&own, g.ws_bytes, s), "cudaMallocAsync(decode workspace)");
+        if (rc) return rc;
+        rc = check_cuda(cudaMemsetAsync(own, 0, (size_t)g.passes * g.rgs * 4u, s), "cudaMemsetAsync(decode counters)");
+        if (rc) { cudaFreeAsync(own, s); return rc; }
+        ws = own;
+    }
+    int rc;
+    if (dk_occupancy() == 4)
+        rc = (L.dtype == PBL_F16) ? launch_decode_t<__half, 4>(L, x, ldx, y, ldy, M, ws, s)
+                                  : launch_decode_t<__nv_bfloat16, 4>(L, x, ldx, y, ldy, M, ws, s);
+    else
+        rc = (L.dtype == PBL_F16) ? launch_decode_t<__half, 3>(L, x, ldx, y, ldy, M, ws, s)
+                                  : launch_decode_t<__nv_bfloat16, 3>(L, x, ldx, y, ldy, M, ws, s);
+    if (own) {
+        const int rf = check_cuda(cudaFreeAsync(own, s), "cudaFreeAsync(decode workspace)");
+        if (!rc) rc = rf;
+    }
+    return rc;
+}
+
+}  // namespace pbl

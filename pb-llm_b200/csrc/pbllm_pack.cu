@@ -114,6 +114,8 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(uint32_t* __restrict_
     if (tid == 0) v[n] = carry;
 }
 
+void launch_scan_counts(uint32_t* v, int64_t n, cudaStream_t s) { scan_counts_kernel<<<1, 1024, 0, s>>>(v, n); }
+
 // ---- salient values -------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(128) pack_vals_kernel(const T* __restrict__ w, int64_t ldw,

@@ -5,6 +5,7 @@ happens inside libpbllm.so (include/pbllm.h)."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -16,6 +17,21 @@ _DT = {torch.float16: _lib.PBL_F16, torch.bfloat16: _lib.PBL_BF16, torch.float32
 
 def _stream(dev) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+DECODE_MAX_M = 16          # calls of at most this many tokens take the decode kernel (pbl_select_kernel == 4)
+_decode_ws = {}            # (device index, stream) -> zero-initialised workspace of the decode kernel's cross-CTA reduction
+
+
+def _decode_workspace(dev, stream_ptr: int, nbytes: int) -> torch.Tensor:
+    """Persistent per-(device, stream) workspace for pbl_linear_forward_ws: zeroed once here, the kernel leaves its
+    arrival counters at zero, so every layer on that stream shares it."""
+    key = (dev.index, stream_ptr)
+    ws = _decode_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 4 << 20), dtype=torch.uint8, device=dev)
+        _decode_ws[key] = ws
+    return ws
 
 
 def pack_sizes(N: int, K: int, groupsize: int, dtype: torch.dtype) -> _lib.PblSizes:
@@ -34,7 +50,8 @@ class PackedLinear:
 
     @classmethod
     def from_dense(cls, w_sim: torch.Tensor, bias: Optional[torch.Tensor] = None,
-                   low_mask: Optional[torch.Tensor] = None, groupsize: int = -1, verify: bool = False):
+                   low_mask: Optional[torch.Tensor] = None, groupsize: int = -1, verify: bool = False,
+                   decode_index: Optional[bool] = None):
         """w_sim: CUDA [N,K] fp16/bf16/fp32. low_mask: bool [N,K], True = binarized position
         (the GPTQ-PB mask-file convention); None = every position may be binarized."""
         if not w_sim.is_cuda:
@@ -50,6 +67,7 @@ class PackedLinear:
             w = w.contiguous()
         N, K = w.shape
         self = cls()
+        self._want_decode_index = decode_index
         self.N, self.K, self.dtype, self.device = N, K, w.dtype, dev
         self.groupsize = K if (groupsize is None or groupsize <= 0 or groupsize >= K) else int(groupsize)
         sz = pack_sizes(N, K, self.groupsize, w.dtype)
@@ -85,9 +103,10 @@ class PackedLinear:
         return self
 
     @classmethod
-    def from_buffers(cls, N, K, groupsize, dtype, planes, vptr, vals, affine, bias=None):
+    def from_buffers(cls, N, K, groupsize, dtype, planes, vptr, vals, affine, bias=None, decode_index=None):
         """Re-create from previously packed device buffers (packed checkpoints / row shards)."""
         self = cls()
+        self._want_decode_index = decode_index
         self.N, self.K, self.dtype, self.device = int(N), int(K), dtype, planes.device
         self.groupsize = K if groupsize <= 0 or groupsize >= K else int(groupsize)
         self.sizes = pack_sizes(N, K, self.groupsize, dtype)
@@ -108,6 +127,42 @@ class PackedLinear:
         h = C.c_void_p()
         _lib.check(_lib.load().pbl_layer_create(C.byref(d), C.byref(h)), "pbl_layer_create")
         self.handle = h
+        self.dsign = self.eptr = self.ent = None
+        want = getattr(self, "_want_decode_index", None)
+        if want is None:
+            want = os.environ.get("PBL_DECODE_INDEX", "1") != "0"
+        if want and self.dtype in (torch.float16, torch.bfloat16):
+            self.build_decode_index()
+
+    def build_decode_index(self):
+        """Second, row-group-major view of the layer with one positioned entry per salient weight
+        (pbl_decode_index_*): what the decode kernel (M <= 16) streams. Derived from the packed buffers."""
+        lib = _lib.load()
+        dev = self.device
+        ds = _lib.PblDecodeSizes()
+        _lib.check(lib.pbl_decode_index_sizes(self.handle, C.byref(ds)), "pbl_decode_index_sizes")
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            eptr = torch.empty(ds.eptr_bytes // 4, dtype=torch.int32, device=dev)
+            _lib.check(lib.pbl_decode_index_count(self.handle, C.c_void_p(eptr.data_ptr()), st), "pbl_decode_index_count")
+            units = int(eptr[-1].item()) & 0xFFFFFFFF
+            dsign = torch.empty(ds.dsign_bytes // 4, dtype=torch.int32, device=dev)
+            ent = torch.zeros(max(units, 1) * 4, dtype=torch.int32, device=dev)
+            _lib.check(lib.pbl_decode_index_fill(self.handle, C.c_void_p(eptr.data_ptr()), C.c_void_p(dsign.data_ptr()),
+                                                 C.c_void_p(ent.data_ptr()), st), "pbl_decode_index_fill")
+            _lib.check(lib.pbl_layer_attach_decode_index(self.handle, C.c_void_p(dsign.data_ptr()), C.c_void_p(eptr.data_ptr()),
+                                                         C.c_void_p(ent.data_ptr())), "pbl_layer_attach_decode_index")
+        self.dsign, self.eptr, self.ent = dsign, eptr, ent
+        self._dws_bytes = int(lib.pbl_decode_workspace_bytes(self.handle, DECODE_MAX_M))
+
+    def drop_decode_index(self):
+        _lib.check(_lib.load().pbl_layer_attach_decode_index(self.handle, None, None, None), "pbl_layer_attach_decode_index")
+        self.dsign = self.eptr = self.ent = None
+
+    def decode_index_bytes(self) -> int:
+        if self.ent is None:
+            return 0
+        return int(self.dsign.numel() * 4 + self.eptr.numel() * 4 + self.ent.numel() * 4)
 
     def __deepcopy__(self, memo):
         b = None if self.bias is None else self.bias.clone()
@@ -137,22 +192,29 @@ class PackedLinear:
         M = x2.shape[0]
         y = out if out is not None else torch.empty((M, self.N), dtype=self.dtype, device=x.device)
         if M:
-            fwd = self._fwd
-            if fwd is None:
-                fwd = self._fwd = _lib.load().pbl_linear_forward
             dev = x.device
             if dev.index != torch.cuda.current_device():
                 with torch.cuda.device(dev):
-                    rc = fwd(self.handle, x2.data_ptr(), x2.stride(0) if M > 1 else self.K, y.data_ptr(), y.stride(0), M,
-                             torch.cuda.current_stream(dev).cuda_stream)
+                    self._launch(x2, y, M, dev)
             else:
-                rc = fwd(self.handle, x2.data_ptr(), x2.stride(0) if M > 1 else self.K, y.data_ptr(), y.stride(0), M,
-                         torch.cuda.current_stream(dev).cuda_stream)
-            if rc:
-                _lib.check(rc, "pbl_linear_forward")
+                self._launch(x2, y, M, dev)
         if out is not None:
             return y
         return y if x.dim() == 2 else y.view(*x.shape[:-1], self.N)
+
+    def _launch(self, x2, y, M, dev):
+        fwd = self._fwd
+        if fwd is None:
+            fwd = self._fwd = _lib.load().pbl_linear_forward_ws
+        st = torch.cuda.current_stream(dev).cuda_stream
+        ws_ptr, ws_bytes = None, 0
+        if M <= DECODE_MAX_M and self.ent is not None and self._dws_bytes:   # decode kernel: persistent workspace
+            ws = _decode_workspace(dev, st, self._dws_bytes)
+            ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
+        rc = fwd(self.handle, x2.data_ptr(), x2.stride(0) if M > 1 else self.K, y.data_ptr(), y.stride(0), M,
+                 ws_ptr, ws_bytes, st)
+        if rc:
+            _lib.check(rc, "pbl_linear_forward")
 
     def bireal_forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None,
                        workspace: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -55,10 +55,13 @@ def test_pack_sizes_host_only():
 
 def test_error_codes_without_compute():
     lib = _lib.load()
-    assert lib.pbl_abi_version() == 2
+    assert lib.pbl_abi_version() == 3
     assert lib.pbl_layer_create(None, None) == -1 and "null" in _lib.last_error()
     assert lib.pbl_linear_forward(None, None, 0, None, 0, 1, None) == -1
     assert lib.pbl_forward_host_workspace(None, 4) == 0
+    assert lib.pbl_linear_forward_ws(None, None, 0, None, 0, 1, None, 0, None) == -1
+    assert lib.pbl_decode_workspace_bytes(None, 8) == 0
+    assert lib.pbl_decode_index_sizes(None, None) == -1 and lib.pbl_layer_attach_decode_index(None, None, None, None) == -1
     assert lib.pbl_launch_count() >= 0
 
 

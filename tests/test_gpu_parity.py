@@ -46,7 +46,8 @@ def rms_rel(y, ref):
 
 
 def forced(p, x, kernel):
-    """Run p.forward with PBL_FORCE_KERNEL=kernel (0 CUDA cores, 1 tcgen05 GEMM, 2 mma.sync skinny)."""
+    """Run p.forward with PBL_FORCE_KERNEL=kernel (0 CUDA cores, 1 tcgen05 GEMM, 2 mma.sync skinny, 3 split-K cluster,
+    4 decode kernel)."""
     os.environ["PBL_FORCE_KERNEL"] = str(kernel)
     try:
         return p.forward(x)
@@ -188,7 +189,7 @@ def test_gemm_tc_matches_oracle(dtype, N, K, gs, M, bias):
     b = rounded(np.random.RandomState(2).standard_normal(N).astype(np.float32) * 0.1, dtype) if bias else None
     x = rounded(make_x(N * 3 + M, (M, K)), dtype)
     p = pb.PackedLinear.from_dense(t(w, dtype), None if b is None else t(b, dtype), t(low), gs)
-    assert p.select_kernel(M) == (2 if M <= 16 else (3 if M <= 128 else 1))   # skinny / split-K cluster / GEMM
+    assert p.select_kernel(M) == (4 if M <= 16 else (3 if M <= 128 else 1))   # decode / split-K cluster / GEMM
     y = forced(p, t(x, dtype), 1)
     if M * N * K <= 4e8:
         ref = orc.linear(x, w, b)                                   # CPU oracle (double accumulate)
@@ -214,7 +215,7 @@ def test_skinny_mma_matches_oracle(dtype, N, K, gs, M, bias):
     b = rounded(np.random.RandomState(3).standard_normal(N).astype(np.float32) * 0.1, dtype) if bias else None
     x = rounded(make_x(N * 5 + M, (M, K)), dtype)
     p = pb.PackedLinear.from_dense(t(w, dtype), None if b is None else t(b, dtype), t(low), gs)
-    assert p.select_kernel(min(M, 16)) == 2
+    assert p.select_kernel(min(M, 16)) == 4          # default route; the skinny kernel stays reachable when forced
     y = forced(p, t(x, dtype), 2)
     ref = orc.linear(x, w, b) if M * N * K <= 4e8 else \
         (t(x).double() @ t(w).double().t() + (0 if b is None else t(b).double())).cpu().numpy()
@@ -267,9 +268,9 @@ def test_gemm_splitk_cluster_matches_oracle(dtype, N, K, gs, M, bias):
     if K % 8 != 0:   # TMA needs 16 B-aligned activation rows: the forced kernel is refused, never silently replaced
         with pytest.raises(RuntimeError, match="does not support"):
             forced(p, t(x, dtype), 3)
-        assert p.select_kernel(M) == 2
+        assert p.select_kernel(M) == 4
         return
-    assert p.select_kernel(M) == (2 if M <= 16 else 3)
+    assert p.select_kernel(M) == (4 if M <= 16 else 3)
     ys = []
     for C in ("", "1", "2", "3", "5", "8"):
         if C:
@@ -554,6 +555,7 @@ def test_dense_salient_chunks_all_kernels(sal_frac, M):
     if M <= 40:
         assert relmax(forced(p, t(x, dtype), 2), ref) <= 1e-3
         assert relmax(forced(p, t(x, dtype), 0), ref) <= 1e-3
+        assert relmax(forced(p, t(x, dtype), 4), ref) <= 1e-3      # > 256 salient per block: the in-loop entry loads
 
 
 def test_degenerate_rows_and_levels():
@@ -571,5 +573,126 @@ def test_degenerate_rows_and_levels():
         p = pb.PackedLinear.from_dense(t(w, torch.float16), None, None, gs)
         assert torch.equal(p.unpack(), t(w, torch.float16))
         ref = orc.linear(x, w)
-        for kern in (0, 2, 3, 1):
+        for kern in (0, 2, 3, 1, 4):
             assert relmax(forced(p, t(x, torch.float16), kern), ref) <= 1e-3, (gs, kern)
+
+
+# ---- the decode kernel (pbl_select_kernel == 4): positioned salient entries, warp-granular stream-K ----------------
+def decode_index_to_dense(p):
+    """Rebuild w_sim from the decode index alone (dsign + eptr + ent + affine), on the host."""
+    TC, rgs = int(p.sizes.tiles_c), int(p.sizes.n_pad) // 32
+    G = int(p.sizes.groups)
+    tpg = TC if G == 1 else p.groupsize // 64
+    dsign = p.dsign.cpu().numpy().view(np.uint32).reshape(rgs * TC, 32, 2)
+    eptr = p.eptr.cpu().numpy().view(np.uint32)
+    ent = p.ent.cpu().numpy().view(np.uint32)
+    aff = p.affine.cpu().numpy().reshape(int(p.sizes.n_pad), G, 2)
+    npdt = np.float16 if p.dtype == torch.float16 else None
+    out = np.zeros((rgs * 32, TC * 64), np.float32)
+    for blk in range(rgs * TC):
+        rg, kb = divmod(blk, TC)
+        g = kb // tpg
+        bits = ((dsign[blk][:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(32, 64)
+        lo, hi = aff[rg * 32:rg * 32 + 32, g, 0:1], aff[rg * 32:rg * 32 + 32, g, 1:2]
+        tile = np.where(bits == 1, hi, lo).astype(np.float32)
+        e = ent[eptr[blk] * 4:eptr[blk + 1] * 4]
+        pos, val = e >> 16, (e & 0xFFFF).astype(np.uint16)
+        r = pos // 128
+        chunk = ((pos % 128) // 16) ^ (r & 7)
+        col = chunk * 8 + (pos % 16) // 2
+        if npdt is not None:
+            v = val.view(np.float16).astype(np.float32)
+        else:
+            v = (val.astype(np.uint32) << 16).view(np.float32)
+        tile[r, col] = v
+        out[rg * 32:rg * 32 + 32, kb * 64:kb * 64 + 64] = tile
+    return out[:p.N, :p.K]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N,K,gs", [(128, 64, -1), (100, 70, -1), (300, 520, -1), (256, 512, 128), (33, 2048, -1)])
+def test_decode_index_reproduces_w_sim_bit_exactly(dtype, N, K, gs):
+    w, low = synth_wsim(N, K, gs, dtype, seed=N + K)
+    p = pb.PackedLinear.from_dense(t(w, dtype), None, t(low), gs)
+    assert p.ent is not None and p.decode_index_bytes() > 0
+    eptr = p.eptr.cpu().numpy().view(np.uint32)
+    assert eptr[0] == 0 and np.all(np.diff(eptr.astype(np.int64)) >= 0)
+    assert int(eptr[-1]) * 4 >= p.nnz and int(eptr[-1]) * 4 <= p.nnz + 3 * (len(eptr) - 1)      # padded to 4 per block
+    assert np.array_equal(decode_index_to_dense(p), w)                                         # integer / bit work: exact
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N,K,gs,M,bias", [(128, 64, -1, 1, False), (96, 160, -1, 3, True), (100, 70, -1, 5, False),
+                                           (300, 520, -1, 8, True), (256, 512, 128, 2, False), (768, 768, -1, 1, True),
+                                           (33, 2048, -1, 9, False), (512, 1024, 256, 16, True), (4096, 4096, -1, 8, False),
+                                           (1024, 11008, -1, 7, False), (264, 1030, -1, 13, True), (2048, 128, -1, 8, True),
+                                           (5000, 64, -1, 4, False), (64, 8192, -1, 16, True), (11008, 4096, -1, 8, False)])
+def test_decode_kernel_matches_oracle(dtype, N, K, gs, M, bias):
+    """Decode kernel incl. ragged N/K (generic activation loads), groups, two token passes (M > 8), layers with fewer
+    blocks than CTAs, row groups finished by one warp (tiny K), row groups split across many CTAs (large K)."""
+    w, low = synth_wsim(N, K, gs, dtype, seed=N + K + M)
+    b = rounded(np.random.RandomState(3).standard_normal(N).astype(np.float32) * 0.1, dtype) if bias else None
+    x = rounded(make_x(N * 5 + M, (M, K)), dtype)
+    p = pb.PackedLinear.from_dense(t(w, dtype), None if b is None else t(b, dtype), t(low), gs)
+    assert p.select_kernel(M) == 4
+    y = p.forward(t(x, dtype))
+    ref = orc.linear(x, w, b) if M * N * K <= 4e8 else \
+        (t(x).double() @ t(w).double().t() + (0 if b is None else t(b).double())).cpu().numpy()
+    assert relmax(y, ref) <= TOL[dtype], (relmax(y, ref), rms_rel(y, ref))
+    assert rms_rel(y, ref) <= TOL[dtype]
+    for _ in range(3):
+        assert torch.equal(y, p.forward(t(x, dtype)))                # deterministic: slots are summed in CTA order
+    y2 = forced(p, t(x, dtype), 2)                                   # same exact tile, other summation order
+    assert relmax(y, y2.float().cpu().numpy()) <= 2 * TOL[dtype]
+
+
+def test_decode_kernel_grid_variants_workspace_and_graph():
+    """Other grid sizes / register budgets give the same bits for a fixed configuration; the library-allocated
+    workspace path (plain pbl_linear_forward) agrees with the persistent one; one workspace serves layers of
+    different shapes back to back; the launch is CUDA-graph capturable."""
+    dtype = torch.float16
+    layers = []
+    for (N, K) in [(768, 768), (3072, 768), (768, 3072), (130, 200)]:
+        w, low = synth_wsim(N, K, -1, dtype, seed=N + K)
+        layers.append((pb.PackedLinear.from_dense(t(w, dtype), None, t(low)), w))
+    xs = {K: t(rounded(make_x(K, (8, K)), dtype), dtype) for K in (768, 3072, 200)}
+    outs = [p.forward(xs[p.K]) for p, _ in layers]
+    for (p, w), y in zip(layers, outs):
+        ref = orc.linear(xs[p.K].float().cpu().numpy(), w)
+        assert relmax(y, ref) <= 1e-3
+    # interleaved replays through the shared workspace
+    for _ in range(3):
+        for (p, _), y in zip(layers, outs):
+            assert torch.equal(p.forward(xs[p.K]), y)
+    # plain pbl_linear_forward: transient workspace from the stream-ordered pool
+    lib = _lib.load()
+    for (p, _), y in zip(layers, outs):
+        x = xs[p.K]
+        y2 = torch.empty_like(y)
+        rc = lib.pbl_linear_forward(p.handle, x.data_ptr(), p.K, y2.data_ptr(), p.N, 8, torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, _lib.last_error()
+        assert torch.equal(y2, y)
+    # CUDA graph capture + replay
+    side = torch.cuda.Stream()
+    p, _ = layers[1]
+    yg = torch.empty_like(outs[1])
+    with torch.cuda.stream(side):
+        p.forward(xs[p.K], out=yg)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(4):
+                p.forward(xs[p.K], out=yg)
+    yg.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(yg, outs[1])
+    # a too-small caller workspace is refused
+    small = torch.zeros(1024, dtype=torch.uint8, device=DEV)
+    rc = lib.pbl_linear_forward_ws(p.handle, xs[p.K].data_ptr(), p.K, yg.data_ptr(), p.N, 8, small.data_ptr(), small.numel(),
+                                   torch.cuda.current_stream().cuda_stream)
+    assert rc == -3 and "workspace" in _lib.last_error()
+    # without a decode index the call falls back to the skinny kernel
+    p.drop_decode_index()
+    assert p.select_kernel(8) == 2
+    assert relmax(p.forward(xs[p.K]), outs[1].float().cpu().numpy()) <= 2e-3
