@@ -21,6 +21,7 @@ def _stream(dev) -> C.c_void_p:
 
 DECODE_MAX_M = 16          # calls of at most this many tokens take the decode kernel (pbl_select_kernel == 4)
 _decode_ws = {}            # (device index, stream) -> zero-initialised workspace of the decode kernel's cross-CTA reduction
+_decode_ws_retired = []    # outgrown workspaces stay alive: captured CUDA graphs may still point at them
 
 
 def _decode_workspace(dev, stream_ptr: int, nbytes: int) -> torch.Tensor:
@@ -29,6 +30,8 @@ def _decode_workspace(dev, stream_ptr: int, nbytes: int) -> torch.Tensor:
     key = (dev.index, stream_ptr)
     ws = _decode_ws.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            _decode_ws_retired.append(ws)
         ws = torch.zeros(max(nbytes, 4 << 20), dtype=torch.uint8, device=dev)
         _decode_ws[key] = ws
     return ws
