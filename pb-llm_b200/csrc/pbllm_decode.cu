@@ -56,6 +56,7 @@ struct Params {
     uint32_t nblocks;     // row groups * tiles_c
     uint32_t rgs;
     uint32_t slots;       // partial slots per row group
+    uint32_t q, rem;      // blocks per warp: nblocks / (grid * 8) and the remainder (the first `rem` warps take one more)
 };
 }  // namespace dk
 
@@ -108,59 +109,74 @@ __device__ __forceinline__ void dk_patch4(const uint32_t tile_s, const uint4 e) 
     sts_u16(tile_s + (e.w >> 16), (uint16_t)e.w);
 }
 
-// kOcc = CTAs per SM the register budget is sized for: 3 -> 85 registers (no spills), 4 -> 64 (one spilled word)
+// kOcc = CTAs per SM the register budget is sized for: 3 -> 85 registers, 4 -> 64
 template <typename T, int kOcc>
 __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk::Params p) {
     using namespace dk;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint32_t s_wlo[kWarps], s_whi[kWarps];
-    __shared__ uint32_t s_fix[3];                 // {slot, expected, last}
+    __shared__ uint32_t s_wlo[kWarps], s_whi[kWarps], s_wrg[kWarps];
+    __shared__ uint32_t s_meta[8];                // {rg_a, rg_b, head split?, slot, expected, tail split?, slot, expected}
+    __shared__ uint32_t s_last[2];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     uint8_t* wsm = smem + wid * kWarpBytes;
     const uint32_t tile_s = smem_u32(wsm);
     const uint32_t xs_s = tile_s + kTileBytes;
     float* head_red = reinterpret_cast<float*>(wsm + kTileBytes + kXBytes);
     float* tail_red = reinterpret_cast<float*>(wsm);      // aliases the tile: written only after the warp's last block
-    uint32_t* eptr_s = reinterpret_cast<uint32_t*>(smem + kWarps * kWarpBytes);
 
-    const uint32_t B = p.nblocks, G = gridDim.x, TC = p.tiles_c;
-    const uint32_t c_lo = (uint32_t)(((uint64_t)blockIdx.x * B) / G), c_hi = (uint32_t)(((uint64_t)(blockIdx.x + 1) * B) / G);
-    uint32_t w_lo, w_hi;
-    {
-        uint32_t v = 0;
-        if (lane < 2) v = (uint32_t)(((uint64_t)(blockIdx.x * kWarps + wid + lane) * B) / ((uint64_t)G * kWarps));
-        w_lo = __shfl_sync(0xffffffffu, v, 0);
-        w_hi = __shfl_sync(0xffffffffu, v, 1);
-    }
+    // ---- work partition (division-free): warp gw owns blocks [gw*q + min(gw,rem), ...), q = B / warps, rem = B % warps ----
+    const uint32_t TC = p.tiles_c, q = p.q, rem = p.rem;
+    auto wstart = [&](uint32_t gw) { return gw * q + min(gw, rem); };
+    const uint32_t gw0 = blockIdx.x * kWarps;
+    const uint32_t c_lo = wstart(gw0), c_hi = wstart(gw0 + kWarps);
+    const uint32_t w_lo = wstart(gw0 + wid), w_hi = wstart(gw0 + wid + 1u);
     const int m0 = blockIdx.y * kTok;
 
     // Programmatic dependent launch: the next kernel in the stream may start its own weight prefetch now; everything
     // below up to griddepcontrol.wait touches only immutable packed weights.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    if (lane == 0) { s_wlo[wid] = w_lo; s_whi[wid] = w_hi; }
-    for (uint32_t i = tid; i <= c_hi - c_lo; i += kThreads) eptr_s[i] = __ldg(p.eptr + c_lo + i);
+    // first loads of this warp's stream: sign words and entry offsets of its run (eptr lives in registers, one per lane)
     const uint2* sgp = p.dsign + (size_t)w_lo * kRgRows + lane;
     uint2 sg = make_uint2(0, 0);
-    if (w_lo < w_hi) sg = __ldg(sgp);
-    __syncthreads();
-
+    uint32_t epr = 0;
+    if (w_lo < w_hi) {
+        sg = __ldg(sgp);
+        if (w_lo + lane <= w_hi) epr = __ldg(p.eptr + w_lo + lane);
+    }
     uint32_t rg = 0, kb = 0;
     if (w_lo < w_hi) { rg = w_lo / TC; kb = w_lo - rg * TC; }
     const uint32_t rg_first = rg;
     const bool grouped = p.groups > 1;
     uint32_t cur_g = grouped ? kb / p.tiles_per_group : 0u;
-    const uint32_t* ep = eptr_s + (w_lo - c_lo);    // eptr of the current block
-    uint32_t eb = 0, n4 = 0;
-    uint4 ea = make_uint4(0, 0, 0, 0), ec = make_uint4(0, 0, 0, 0);
     float2 af = make_float2(0.f, 0.f);
+    if (w_lo < w_hi) af = __ldg(p.affine + (size_t)(rg * kRgRows + lane) * p.groups + cur_g);
+
+    if (lane == 0) { s_wlo[wid] = w_lo; s_whi[wid] = w_hi; s_wrg[wid] = rg_first; }
+    if (tid == 0) {                               // which of this CTA's row groups are shared with other CTAs, and how
+        const uint32_t rg_a = c_lo / TC, rg_b = (c_hi - 1u) / TC;
+        auto owner = [&](uint32_t b) {            // CTA whose run contains block b
+            const uint32_t cut = rem * (q + 1u);
+            const uint32_t gw = b < cut ? b / (q + 1u) : rem + (b - cut) / q;
+            return gw / kWarps;
+        };
+        s_meta[0] = rg_a; s_meta[1] = rg_b;
+        const bool hs = c_lo > rg_a * TC || c_hi < rg_a * TC + TC;
+        const bool ts = rg_b != rg_a && c_hi < rg_b * TC + TC;
+        s_meta[2] = hs; s_meta[5] = ts;
+        if (hs) { const uint32_t f = owner(rg_a * TC); s_meta[3] = blockIdx.x - f; s_meta[4] = owner(rg_a * TC + TC - 1u) - f + 1u; }
+        if (ts) { const uint32_t f = owner(rg_b * TC); s_meta[6] = blockIdx.x - f; s_meta[7] = owner(rg_b * TC + TC - 1u) - f + 1u; }
+    }
+
+    uint32_t ci = 0;                               // index of the current block in the eptr register chunk
+    uint32_t eb = __shfl_sync(0xffffffffu, epr, 0), n4 = __shfl_sync(0xffffffffu, epr, 1) - eb;
+    uint4 ea = make_uint4(0, 0, 0, 0), ec = make_uint4(0, 0, 0, 0);
     if (w_lo < w_hi) {
-        eb = ep[0];
-        n4 = ep[1] - eb;
         const uint4* e = p.ent + (eb + lane);
         if (lane < n4) ea = __ldg(e);
         if (lane + 32u < n4) ec = __ldg(e + 32);
-        af = __ldg(p.affine + (size_t)(rg * kRgRows + lane) * p.groups + cur_g);
+    } else {
+        n4 = 0;
     }
     uint32_t LL, DD;
     {
@@ -187,15 +203,15 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
             xa = __ldg(p4);
             xb = __ldg(p4 + 1);
         } else {
-            const uint16_t* q = reinterpret_cast<const uint16_t*>(xbytes + xoff);
+            const uint16_t* qx = reinterpret_cast<const uint16_t*>(xbytes + xoff);
             const int col = (int)(kblk * kTileCols + 16 * xseg);
             uint32_t w[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int cc = col + 2 * i;
                 uint32_t v = 0;
-                if (x_tok_ok && cc < p.K) v = (uint32_t)q[2 * i];
-                if (x_tok_ok && cc + 1 < p.K) v |= (uint32_t)q[2 * i + 1] << 16;
+                if (x_tok_ok && cc < p.K) v = (uint32_t)qx[2 * i];
+                if (x_tok_ok && cc + 1 < p.K) v |= (uint32_t)qx[2 * i + 1] << 16;
                 w[i] = v;
             }
             xa = make_uint4(w[0], w[1], w[2], w[3]);
@@ -213,9 +229,9 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     const uint32_t g4 = lane >> 2, t4 = lane & 3u;
     uint32_t lm_q[4];                                                             // ldmatrix row address per k16 step
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        lm_q[q] = lm_base0 ^ ((uint32_t)q << 5);
-        asm volatile("" : "+r"(lm_q[q]));                                         // keep in a register (no rematerialisation)
+    for (int qi = 0; qi < 4; ++qi) {
+        lm_q[qi] = lm_base0 ^ ((uint32_t)qi << 5);
+        asm volatile("" : "+r"(lm_q[qi]));                                        // keep in a register (no rematerialisation)
     }
     uint32_t xl0 = xl_base, xl1 = xl_base ^ 64u, brow_r = brow, xst_r = xst0;
     asm volatile("" : "+r"(xl0), "+r"(xl1), "+r"(brow_r), "+r"(xst_r));
@@ -264,9 +280,12 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
         if (lane + 32u < n4) dk_patch4(tile_s, ec);
         for (uint32_t i = 64u + lane; i < n4; i += 32u) dk_patch4(tile_s, __ldg(p.ent + (eb + i)));   // rare: > 256 salient in a block
         if (more) {
-            ++ep;
-            eb = ep[0];
-            n4 = ep[1] - eb;
+            if (++ci == 31u) {                          // rare: refill the eptr registers (runs longer than 31 blocks)
+                ci = 0;
+                if (blk + 1u + lane <= w_hi) epr = __ldg(p.eptr + blk + 1u + lane);
+            }
+            eb = __shfl_sync(0xffffffffu, epr, ci);
+            n4 = __shfl_sync(0xffffffffu, epr, ci + 1u) - eb;
             const uint4* e = p.ent + (eb + lane);
             asm volatile("" : "+l"(e));                 // one address computation for both predicated loads
             if (lane < n4) ea = __ldg(e);
@@ -286,11 +305,10 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
             dk_ldsm4(jj ? xl1 : xl0, b[0], b[1], b[2], b[3]);
 #pragma unroll
             for (int qq = 0; qq < 2; ++qq) {
-                const uint32_t q = 2u * jj + qq;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     uint32_t a0, a1, a2, a3;
-                    dk_ldsm4(lm_q[q] + (uint32_t)h * 2048u, a0, a1, a2, a3);
+                    dk_ldsm4(lm_q[2 * jj + qq] + (uint32_t)h * 2048u, a0, a1, a2, a3);
                     dk_mma<T>(acc[h], a0, a1, a2, a3, b[2 * qq], b[2 * qq + 1]);
                 }
             }
@@ -333,58 +351,64 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
         }
     }
 
-    // ---- cross-warp, then cross-CTA reduction of the partial row groups -------------------------------------------
+    // ---- cross-warp reduction in shared memory; row groups shared with other CTAs go through the workspace ----------
     __syncthreads();
     if (c_lo >= c_hi) return;
-    const uint32_t rg_a = c_lo / TC, rg_b = (c_hi - 1) / TC;
+    const uint32_t rg_a = s_meta[0], rg_b = s_meta[1];
     const uint32_t om = tid >> 5, orr = tid & 31u;          // this thread's output: token om, row orr of the row group
+    T* yout = reinterpret_cast<T*>(p.y) + (int64_t)(m0 + om) * p.ldy;
+    const bool tok_ok = (m0 + (int)om) < p.M;
+    float v_split[2] = {0.f, 0.f};                          // [0] head row group, [1] tail row group (when shared)
     for (uint32_t r = rg_a; r <= rg_b; ++r) {
         const uint32_t r_lo = r * TC, r_hi = r_lo + TC;
         const uint32_t seg_lo = max(c_lo, r_lo), seg_hi = min(c_hi, r_hi);
         float v = 0.f;
-        uint32_t contributors = 0;
-        bool single_whole = false;
+        bool any = false, single_whole = false;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
             const uint32_t wl = s_wlo[w], wh = s_whi[w];
             if (wl < wh && wl < seg_hi && wh > seg_lo) {
-                ++contributors;
                 if (wl <= r_lo && wh >= r_hi) { single_whole = true; continue; }   // that warp stored the row group itself
-                const float* src = reinterpret_cast<const float*>(smem + w * kWarpBytes + ((wl / TC == r) ? (kTileBytes + kXBytes) : 0));
-                v += src[tid];
+                any = true;
+                v += reinterpret_cast<const float*>(smem + w * kWarpBytes + ((s_wrg[w] == r) ? (kTileBytes + kXBytes) : 0))[tid];
             }
         }
-        if (single_whole || contributors == 0) continue;
-        const int orow = (int)(r * kRgRows + orr);
-        const bool ok = (orow < p.N) && (m0 + (int)om < p.M);
+        if (single_whole || !any) continue;
         if (seg_lo == r_lo && seg_hi == r_hi) {              // the whole row group lives in this CTA
-            if (ok) reinterpret_cast<T*>(p.y)[(int64_t)(m0 + om) * p.ldy + orow] = from_f32<T>((p.bias ? p.bias[orow] : 0.f) + v);
-            continue;
+            const int orow = (int)(r * kRgRows + orr);
+            if (tok_ok && orow < p.N) yout[orow] = from_f32<T>((p.bias ? p.bias[orow] : 0.f) + v);
+        } else if (r == rg_a) {
+            v_split[0] = v;
+        } else {
+            v_split[1] = v;
         }
-        // split across CTAs: park the partial in this CTA's slot, the last arriver sums the slots in CTA order
-        if (tid == 0) {
-            const uint32_t first = (uint32_t)((((uint64_t)r_lo + 1) * G - 1) / B);      // CTA owning block r_lo
-            const uint32_t lastc = (uint32_t)((((uint64_t)r_hi) * G - 1) / B);          // CTA owning block r_hi - 1
-            s_fix[0] = blockIdx.x - first;
-            s_fix[1] = lastc - first + 1u;
-        }
-        __syncthreads();
-        const uint32_t slot = s_fix[0], expected = s_fix[1];
-        float* part = p.ws_part + (((size_t)blockIdx.y * p.rgs + r) * p.slots) * kOut;
-        uint32_t* cnt = p.ws_cnt + (size_t)blockIdx.y * p.rgs + r;
-        part[(size_t)slot * kOut + tid] = v;
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) s_fix[2] = (atomicAdd(cnt, 1u) + 1u == expected) ? 1u : 0u;
-        __syncthreads();
-        if (s_fix[2]) {
-            __threadfence();
-            float s = (p.bias && orow < p.N) ? p.bias[orow] : 0.f;
-            for (uint32_t k = 0; k < expected; ++k) s += __ldcg(part + (size_t)k * kOut + tid);
-            if (ok) reinterpret_cast<T*>(p.y)[(int64_t)(m0 + om) * p.ldy + orow] = from_f32<T>(s);
-            if (tid == 0) *cnt = 0u;                         // ready for the next kernel that uses this workspace
-        }
-        __syncthreads();                                     // s_fix is reused by the next row group
+    }
+    const bool hs = s_meta[2] != 0u, ts = s_meta[5] != 0u;
+    if (!hs && !ts) return;
+    // shared row groups: park the partial in this CTA's slot; the last arriver sums the slots in CTA order (deterministic)
+    float* part_h = p.ws_part + (((size_t)blockIdx.y * p.rgs + rg_a) * p.slots) * kOut;
+    float* part_t = p.ws_part + (((size_t)blockIdx.y * p.rgs + rg_b) * p.slots) * kOut;
+    uint32_t* cnt_h = p.ws_cnt + (size_t)blockIdx.y * p.rgs + rg_a;
+    uint32_t* cnt_t = p.ws_cnt + (size_t)blockIdx.y * p.rgs + rg_b;
+    if (hs) part_h[(size_t)s_meta[3] * kOut + tid] = v_split[0];
+    if (ts) part_t[(size_t)s_meta[6] * kOut + tid] = v_split[1];
+    __syncthreads();                                         // every partial of this CTA is written ...
+    if (tid < 2u && (tid == 0u ? hs : ts)) {                 // ... and published by one acq_rel arrival per row group
+        uint32_t old;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(tid == 0u ? cnt_h : cnt_t) : "memory");
+        s_last[tid] = (old + 1u == s_meta[tid == 0u ? 4 : 7]) ? 1u : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+        if (!(f == 0 ? hs : ts) || !s_last[f]) continue;
+        const uint32_t r = f == 0 ? rg_a : rg_b, expected = s_meta[f == 0 ? 4 : 7];
+        const float* part = f == 0 ? part_h : part_t;
+        const int orow = (int)(r * kRgRows + orr);
+        float s = (p.bias && orow < p.N) ? p.bias[orow] : 0.f;
+        for (uint32_t k = 0; k < expected; ++k) s += __ldcg(part + (size_t)k * kOut + tid);
+        if (tok_ok && orow < p.N) yout[orow] = from_f32<T>(s);
+        if (tid == 0) *(f == 0 ? cnt_h : cnt_t) = 0u;        // ready for the next kernel that uses this workspace
     }
 }
 
@@ -485,15 +509,19 @@ static int dk_num_sms() {
     return sms[dev] > 0 ? sms[dev] : 148;
 }
 
-struct DecodeGeom { uint32_t nblocks, rgs, grid, slots, passes; size_t ws_bytes; };
+struct DecodeGeom { uint32_t nblocks, rgs, grid, slots, passes, q, rem; size_t ws_bytes; };
 
 static DecodeGeom decode_geom(const Layer& L, int64_t M) {
     DecodeGeom g;
     g.rgs = (uint32_t)(L.tiles_r * kRgPerTile);
     g.nblocks = g.rgs * (uint32_t)L.tiles_c;
     const uint32_t want = (uint32_t)(dk_num_sms() * dk_ctas_per_sm());
-    g.grid = g.nblocks < want ? g.nblocks : want;
-    g.slots = (uint32_t)(((uint64_t)L.tiles_c * g.grid + g.nblocks - 1) / g.nblocks) + 1u;
+    const uint32_t cap = g.nblocks / dk::kWarps > 0 ? g.nblocks / dk::kWarps : 1u;   // at least one block per warp
+    g.grid = cap < want ? cap : want;
+    g.q = g.nblocks / (g.grid * dk::kWarps);
+    g.rem = g.nblocks % (g.grid * dk::kWarps);
+    // a CTA's run is at least 8*q blocks long, so a row group (tiles_c blocks) meets at most this many CTAs
+    g.slots = g.q ? ((uint32_t)L.tiles_c + 8u * g.q - 1u) / (8u * g.q) + 1u : 2u;
     g.passes = (uint32_t)((M + dk::kTok - 1) / dk::kTok);
     g.ws_bytes = (size_t)dk::kCntCap * 4u + (size_t)g.passes * g.rgs * g.slots * dk::kOut * 4u;
     return g;
@@ -516,9 +544,7 @@ size_t decode_workspace_bytes(const Layer& L, int64_t M) {
 template <typename T, int kOcc>
 static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws, cudaStream_t s) {
     const DecodeGeom g = decode_geom(L, M);
-    const uint32_t max_run = (g.nblocks + g.grid - 1) / g.grid + 1u;               // blocks in a CTA's run (upper bound)
-    const int smem = dk::kWarps * dk::kWarpBytes + (int)(((max_run + 2u) * 4u + 15u) & ~15u);
-    if (smem > 200 * 1024) { set_error("decode kernel: layer too large for the eptr staging area"); return PBL_ERR_UNSUPPORTED; }
+    const int smem = dk::kWarps * dk::kWarpBytes;
     static int attr_smem_dev[64] = {};   // function attributes are per device
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
@@ -536,7 +562,7 @@ static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, 
     p.ws_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + (size_t)dk::kCntCap * 4u);
     p.M = (int)M; p.N = (int)L.N; p.K = (int)L.K;
     p.tiles_c = (uint32_t)L.tiles_c; p.groups = (uint32_t)L.groups; p.tiles_per_group = (uint32_t)L.tiles_per_group;
-    p.nblocks = g.nblocks; p.rgs = g.rgs; p.slots = g.slots;
+    p.nblocks = g.nblocks; p.rgs = g.rgs; p.slots = g.slots; p.q = g.q; p.rem = g.rem;
 
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(g.grid, g.passes);
