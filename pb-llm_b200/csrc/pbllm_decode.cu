@@ -33,9 +33,8 @@ constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kTok = 8;                       // tokens per pass (mma N)
 constexpr int kTileBytes = kRgRows * kTileCols * 2;   // 4096: the warp's 32x64 16-bit weight tile (128B rows, swizzled)
-constexpr int kXBytes = kTok * kTileCols * 2;         // 1024: the block's activations, 8 token rows of 128 B, swizzled
 constexpr int kHeadBytes = kRgRows * kTok * 4;        // 1024: the warp's head-segment partial (fp32 [8 tokens][32 rows])
-constexpr int kWarpBytes = kTileBytes + kXBytes + kHeadBytes;   // 6144
+constexpr int kWarpBytes = kTileBytes + kHeadBytes;   // 5120
 constexpr int kOut = kRgRows * kTok;          // 256 outputs per (row group, token pass) == kThreads
 static_assert(kOut == kThreads, "one thread per output in the cross-warp reduction");
 constexpr uint32_t kCntCap = 16384;           // arrival counters at the head of the workspace (u32 each)
@@ -81,23 +80,30 @@ __device__ __forceinline__ void dk_ldsm4(uint32_t addr, uint32_t& r0, uint32_t& 
                  : "memory");
 }
 
-// 64 sign bits of one weight row -> 64 exact {lo,hi} 16-bit values, written as 8 swizzled 16 B chunks (chunk c holds
-// columns 8c..8c+7 at row + ((c ^ (row & 7)) << 4); `brow` already carries (row & 7) << 4, so that is brow ^ (c << 4)):
-// the same PRMT byte-sign replicate + LOP3 select as expand_row.
+// Tile layout.  The warp's 32x64 tile has 128-byte rows of eight 16-byte chunks, chunk pc stored at
+// row*128 + ((pc ^ (row & 7)) << 4) (conflict-free for the row-per-lane stores and for ldmatrix).  Columns are PERMUTED
+// inside a row so that the activations never go through shared memory: chunk pc, 32-bit word t holds the logical
+// columns 16t + 2pc + {0,1}.  ldmatrix then hands lane (g, t) of k16-step q exactly the columns 16t + 4q + {0,1} (a0/a1)
+// and 16t + 4q + {2,3} (a2/a3) -- the columns of words 2q and 2q+1 of the 16 consecutive activations that lane loaded
+// from global memory (token g, columns 16t..16t+15), which therefore ARE its B fragments.
+//
+// 64 sign bits of one weight row -> 64 exact {lo,hi} 16-bit values, 8 STS.128: PRMT byte-sign replicate + LOP3 select
+// as in expand_row; `brow` already carries (row & 7) << 4, so chunk pc is at brow ^ (pc << 4).
 __device__ __forceinline__ void dk_expand_dense(const uint2 sg, const uint32_t LL, const uint32_t DD, const uint32_t brow) {
+    uint32_t X[2][8];
 #pragma unroll
-    for (int wd = 0; wd < 2; ++wd) {
-        const uint32_t s = wd ? sg.y : sg.x;
-        const uint32_t X0 = s, X1 = s << 1, X2 = s << 2, X3 = s << 3, X4 = s << 4, X5 = s << 5, X6 = s << 6, X7 = s << 7;
+    for (int k = 0; k < 8; ++k) { X[0][k] = sg.x << k; X[1][k] = sg.y << k; }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const uint32_t sel = 0x8888u | (uint32_t)c | ((uint32_t)c << 4) | ((uint32_t)(4 + c) << 8) | ((uint32_t)(4 + c) << 12);
-            const uint32_t h0 = sel_xor_and(LL, DD, prmt(X7, X6, sel));
-            const uint32_t h1 = sel_xor_and(LL, DD, prmt(X5, X4, sel));
-            const uint32_t h2 = sel_xor_and(LL, DD, prmt(X3, X2, sel));
-            const uint32_t h3 = sel_xor_and(LL, DD, prmt(X1, X0, sel));
-            sts_v4(brow ^ ((uint32_t)(wd * 4 + c) << 4), h0, h1, h2, h3);
+    for (int pc = 0; pc < 8; ++pc) {
+        const int j = 2 * (pc & 3), by0 = pc >> 2;      // bit 2pc (+16 for odd t) of the sign word: byte by0 (+2), bit j
+        uint32_t h[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const uint32_t by = (uint32_t)(by0 + 2 * (t & 1));
+            const uint32_t sel = 0x8888u | by | (by << 4) | ((4u + by) << 8) | ((4u + by) << 12);
+            h[t] = sel_xor_and(LL, DD, prmt(X[t >> 1][7 - j], X[t >> 1][6 - j], sel));
         }
+        sts_v4(brow ^ ((uint32_t)pc << 4), h[0], h[1], h[2], h[3]);
     }
 }
 
@@ -120,8 +126,7 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     uint8_t* wsm = smem + wid * kWarpBytes;
     const uint32_t tile_s = smem_u32(wsm);
-    const uint32_t xs_s = tile_s + kTileBytes;
-    float* head_red = reinterpret_cast<float*>(wsm + kTileBytes + kXBytes);
+    float* head_red = reinterpret_cast<float*>(wsm + kTileBytes);
     float* tail_red = reinterpret_cast<float*>(wsm);      // aliases the tile: written only after the warp's last block
 
     // ---- work partition (division-free): warp gw owns blocks [gw*q + min(gw,rem), ...), q = B / warps, rem = B % warps ----
@@ -171,12 +176,15 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     uint32_t ci = 0;                               // index of the current block in the eptr register chunk
     uint32_t eb = __shfl_sync(0xffffffffu, epr, 0), n4 = __shfl_sync(0xffffffffu, epr, 1) - eb;
     uint4 ea = make_uint4(0, 0, 0, 0), ec = make_uint4(0, 0, 0, 0);
+    // the first min(n4, 64) units of a block sit in two register sets of h1 = ceil/2 and the rest: unit `lane` and unit
+    // `h1 + lane` (the index builder deals entries to units so that each of the 8 patch stores is bank-conflict free)
+    uint32_t n1 = min(n4, 64u), h1 = (n1 + 1u) >> 1;
     if (w_lo < w_hi) {
         const uint4* e = p.ent + (eb + lane);
-        if (lane < n4) ea = __ldg(e);
-        if (lane + 32u < n4) ec = __ldg(e + 32);
+        if (lane < h1) ea = __ldg(e);
+        if (lane + h1 < n1) ec = __ldg(e + h1);
     } else {
-        n4 = 0;
+        n4 = n1 = h1 = 0;
     }
     uint32_t LL, DD;
     {
@@ -222,10 +230,8 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     // shared-memory addresses of this lane
     const uint32_t r7 = lane & 7u;
     const uint32_t brow = (tile_s + lane * 128u) | (r7 << 4);                     // my weight row; chunk c lives at brow ^ (c << 4)
-    const uint32_t xst0 = xs_s + xtok * 128u + (((2u * xseg) ^ xtok) << 4);       // my two 16 B activation chunks
     const uint32_t lm_row = (lane & 7u) + ((lane >> 3) & 1u) * 8u;                // A fragments (weights)
     const uint32_t lm_base0 = tile_s + lm_row * 128u + (((lane >> 4) ^ (lm_row & 7u)) << 4);
-    const uint32_t xl_base = xs_s + r7 * 128u + (((lane >> 3) ^ r7) << 4);        // B fragments (activations)
     const uint32_t g4 = lane >> 2, t4 = lane & 3u;
     uint32_t lm_q[4];                                                             // ldmatrix row address per k16 step
 #pragma unroll
@@ -233,8 +239,8 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
         lm_q[qi] = lm_base0 ^ ((uint32_t)qi << 5);
         asm volatile("" : "+r"(lm_q[qi]));                                        // keep in a register (no rematerialisation)
     }
-    uint32_t xl0 = xl_base, xl1 = xl_base ^ 64u, brow_r = brow, xst_r = xst0;
-    asm volatile("" : "+r"(xl0), "+r"(xl1), "+r"(brow_r), "+r"(xst_r));
+    uint32_t brow_r = brow;
+    asm volatile("" : "+r"(brow_r));
 
     float acc[2][4];
 #pragma unroll
@@ -274,10 +280,11 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
 
         __syncwarp();                                   // the previous block's ldmatrix reads are done
         dk_expand_dense(sg, LL, DD, brow_r);
-        if (more) { sgp += kRgRows; sg = __ldg(sgp); }
+        sgp += more ? kRgRows : 0;                      // unconditional reload (the last block re-reads itself): the load
+        sg = __ldg(sgp);                                // must land in `sg` directly, not in a temporary that is moved at once
         __syncwarp();                                   // dense rows land before other lanes patch them
-        if (lane < n4) dk_patch4(tile_s, ea);
-        if (lane + 32u < n4) dk_patch4(tile_s, ec);
+        if (lane < h1) dk_patch4(tile_s, ea);
+        if (lane + h1 < n1) dk_patch4(tile_s, ec);
         for (uint32_t i = 64u + lane; i < n4; i += 32u) dk_patch4(tile_s, __ldg(p.ent + (eb + i)));   // rare: > 256 salient in a block
         if (more) {
             if (++ci == 31u) {                          // rare: refill the eptr registers (runs longer than 31 blocks)
@@ -286,33 +293,32 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
             }
             eb = __shfl_sync(0xffffffffu, epr, ci);
             n4 = __shfl_sync(0xffffffffu, epr, ci + 1u) - eb;
+            n1 = min(n4, 64u);
+            h1 = (n1 + 1u) >> 1;
             const uint4* e = p.ent + (eb + lane);
             asm volatile("" : "+l"(e));                 // one address computation for both predicated loads
-            if (lane < n4) ea = __ldg(e);
-            if (lane + 32u < n4) ec = __ldg(e + 32);
+            if (lane < h1) ea = __ldg(e);
+            if (lane + h1 < n1) ec = __ldg(e + h1);
         }
-        sts_v4(xst_r, xa.x, xa.y, xa.z, xa.w);
-        sts_v4(xst_r ^ 16u, xb.x, xb.y, xb.z, xb.w);
-        ++kb;
-        const bool rg_end = kb == TC;
-        xoff = rg_end ? xoff_row : xoff + kTileCols * 2u;
-        if (more) load_x(rg_end ? 0u : kb, xa, xb);
-        __syncwarp();                                   // tile and activations visible to the whole warp
+        __syncwarp();                                   // the tile is complete and visible to the whole warp
 
+        // tensor cores: A fragments by ldmatrix from the tile, B fragments straight from the activation registers
+        {
+            const uint32_t xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-            uint32_t b[4];
-            dk_ldsm4(jj ? xl1 : xl0, b[0], b[1], b[2], b[3]);
-#pragma unroll
-            for (int qq = 0; qq < 2; ++qq) {
+            for (int qi = 0; qi < 4; ++qi) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     uint32_t a0, a1, a2, a3;
-                    dk_ldsm4(lm_q[2 * jj + qq] + (uint32_t)h * 2048u, a0, a1, a2, a3);
-                    dk_mma<T>(acc[h], a0, a1, a2, a3, b[2 * qq], b[2 * qq + 1]);
+                    dk_ldsm4(lm_q[qi] + (uint32_t)h * 2048u, a0, a1, a2, a3);
+                    dk_mma<T>(acc[h], a0, a1, a2, a3, xw[2 * qi], xw[2 * qi + 1]);
                 }
             }
         }
+        ++kb;
+        const bool rg_end = kb == TC;
+        xoff = rg_end ? xoff_row : xoff + kTileCols * 2u;
+        load_x(rg_end ? 0u : kb, xa, xb);               // unconditional: the address after the last block is still inside x
 
         // ---- end of this warp's part of the row group? -----------------------------------------------------
         if (rg_end || !more) {
@@ -370,7 +376,7 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
             if (wl < wh && wl < seg_hi && wh > seg_lo) {
                 if (wl <= r_lo && wh >= r_hi) { single_whole = true; continue; }   // that warp stored the row group itself
                 any = true;
-                v += reinterpret_cast<const float*>(smem + w * kWarpBytes + ((s_wrg[w] == r) ? (kTileBytes + kXBytes) : 0))[tid];
+                v += reinterpret_cast<const float*>(smem + w * kWarpBytes + ((s_wrg[w] == r) ? kTileBytes : 0))[tid];
             }
         }
         if (single_whole || !any) continue;
@@ -426,6 +432,11 @@ __global__ void decode_index_count_kernel(const uint32_t* __restrict__ vptr, uin
 }
 
 // pass 2: sign words and entries. CTA = one 128x64 plane tile, warp = one 32-row group, lane = row.
+// Entry order inside a block is chosen for the kernel's patch stores: store j of register set a writes the entries at
+// slots 4*(a*h1 + lane) + j, lane = 0..31 -- a "group" of up to 32 entries that should fall in 32 different shared-memory
+// banks.  Entries are ranked by (bank, row, column) and rank k goes to group k % 8, position k / 8: the <= 8 entries of
+// one bank land in 8 different groups.  (A row touches each bank at most twice, so per-bank counts come from two
+// ballots.)  Blocks with more than 256 entries keep ranks >= 256 in rank order behind the first 64 units.
 __global__ void __launch_bounds__(128) decode_index_fill_kernel(const uint4* __restrict__ planes, const uint32_t* __restrict__ vptr,
                                                                 const uint16_t* __restrict__ vals, const uint32_t* __restrict__ eptr,
                                                                 uint32_t tiles_c, uint2* __restrict__ dsign,
@@ -440,23 +451,54 @@ __global__ void __launch_bounds__(128) decode_index_fill_kernel(const uint4* __r
     const uint32_t vbase = vptr[old], cnt = vptr[old + 1] - vbase;
     if (cnt == 0) return;                                   // warp-uniform
     const uint32_t mine = (uint32_t)(__popc(pw.z) + __popc(pw.w));
-    uint32_t off = warp_excl_scan(mine, lane);
+    const uint32_t voff = warp_excl_scan(mine, lane);       // my row's first value in the packed (row, column) order
     uint32_t* dst = ent + (size_t)eptr[blk] * 4u;
-    const bool owns_last = mine > 0 && off + mine == cnt;   // the last row with salient entries also writes the padding
-    uint32_t e = 0;
-#pragma unroll
+    const uint32_t n4 = (cnt + 3u) / 4u, n1 = min(n4, 64u), h1 = (n1 + 1u) >> 1;
+
+    // my row's entries and the banks they hit (each bank at most twice per row: two columns per 32-bit word)
+    uint32_t my_e[64];
+    uint32_t m1 = 0, m2 = 0, ne = 0;
+#pragma unroll 1
     for (int wd = 0; wd < 2; ++wd) {
         uint32_t m = wd ? pw.w : pw.z;
         while (m) {
             const uint32_t col = (uint32_t)(__ffs(m) - 1) + 32u * wd;
             m &= m - 1u;
-            const uint32_t pos = lane * 128u + ((((col >> 3) ^ (lane & 7u))) << 4) + (col & 7u) * 2u;   // byte offset in the swizzled tile
-            e = (pos << 16) | (uint32_t)vals[vbase + off];
-            dst[off++] = e;
+            const uint32_t pc = (col >> 1) & 7u;                                             // chunk, word, half: see "Tile layout"
+            const uint32_t pos = lane * 128u + ((pc ^ (lane & 7u)) << 4) + (col >> 4) * 4u + (col & 1u) * 2u;
+            my_e[ne] = (pos << 16) | (uint32_t)vals[vbase + voff + ne];
+            ++ne;
+            const uint32_t bit = 1u << ((pos >> 2) & 31u);
+            m2 |= m1 & bit;
+            m1 |= bit;
         }
     }
-    if (owns_last)
-        for (uint32_t k = cnt; k < ((cnt + 3u) & ~3u); ++k) dst[k] = e;
+    // rank of my first entry in every bank: entries of lower banks + entries of this bank in lower rows
+    uint16_t start[32];
+    uint32_t base = 0;
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll 1
+    for (int bnk = 0; bnk < 32; ++bnk) {
+        const uint32_t b1 = __ballot_sync(0xffffffffu, (m1 >> bnk) & 1u), b2 = __ballot_sync(0xffffffffu, (m2 >> bnk) & 1u);
+        start[bnk] = (uint16_t)(base + __popc(b1 & lt) + __popc(b2 & lt));
+        base += __popc(b1) + __popc(b2);
+    }
+    // every slot first gets a copy of one real entry (padding must be an idempotent store), then the real entries land
+    const uint32_t first_lane = (uint32_t)__ffs(__ballot_sync(0xffffffffu, ne > 0)) - 1u;
+    const uint32_t pad = __shfl_sync(0xffffffffu, ne ? my_e[0] : 0u, first_lane);
+    for (uint32_t sl = lane; sl < n4 * 4u; sl += 32u) dst[sl] = pad;
+    __syncwarp();
+#pragma unroll 1
+    for (uint32_t i = 0; i < ne; ++i) {
+        const uint32_t e = my_e[i];
+        const uint32_t k = start[(e >> 18) & 31u]++;
+        uint32_t slot = k;
+        if (k < 256u) {
+            const uint32_t g = k & 7u, idx = k >> 3;
+            slot = 4u * ((g >> 2) * h1 + idx) + (g & 3u);
+        }
+        dst[slot] = e;
+    }
 }
 
 void launch_scan_counts(uint32_t* v, int64_t n, cudaStream_t s);   // pbllm_pack.cu

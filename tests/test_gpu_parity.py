@@ -597,9 +597,9 @@ def decode_index_to_dense(p):
         tile = np.where(bits == 1, hi, lo).astype(np.float32)
         e = ent[eptr[blk] * 4:eptr[blk + 1] * 4]
         pos, val = e >> 16, (e & 0xFFFF).astype(np.uint16)
-        r = pos // 128
-        chunk = ((pos % 128) // 16) ^ (r & 7)
-        col = chunk * 8 + (pos % 16) // 2
+        r = pos // 128                                    # tile layout of pbllm_decode.cu: chunk pc, word t, half e
+        pc = ((pos % 128) // 16) ^ (r & 7)                # <-> logical column 16 t + 2 pc + e
+        col = 16 * ((pos % 16) // 4) + 2 * pc + (pos % 4) // 2
         if npdt is not None:
             v = val.view(np.float16).astype(np.float32)
         else:
@@ -696,3 +696,27 @@ def test_decode_kernel_workspace_sharing_and_graph():
     p.drop_decode_index()
     assert p.select_kernel(8) == 2
     assert relmax(p.forward(xs[p.K]), outs[1].float().cpu().numpy()) <= 2e-3
+
+
+def test_decode_index_entry_order_spreads_banks():
+    """The index builder deals a block's entries to the kernel's 8 patch stores by shared-memory bank: with <= 8
+    entries per bank every store is conflict free; at 10 % density the average store must need well under the ~3
+    wavefronts of the row-major order."""
+    w, low = synth_wsim(256, 512, -1, torch.float16, seed=5)
+    p = pb.PackedLinear.from_dense(t(w, torch.float16), None, t(low))
+    eptr = p.eptr.cpu().numpy().view(np.uint32)
+    ent = p.ent.cpu().numpy().view(np.uint32)
+    waves, stores = 0, 0
+    for blk in range(len(eptr) - 1):
+        n4 = int(eptr[blk + 1] - eptr[blk])
+        if n4 == 0 or n4 > 64:
+            continue
+        e = ent[eptr[blk] * 4:eptr[blk + 1] * 4].reshape(n4, 4)
+        h1 = (n4 + 1) // 2
+        for units in (e[:h1], e[h1:]):
+            for j in range(4):
+                pos = units[:, j] >> 16
+                words = np.unique(pos // 4)                      # lanes writing the same word do not conflict
+                waves += np.bincount(words % 32).max()
+                stores += 1
+    assert stores > 0 and waves / stores < 2.4, waves / stores
