@@ -14,7 +14,7 @@
 //    With explicit positions the salient patch is lane-balanced: entry e of a block is handled by lane e/4 % 32,
 //    3 instructions per entry, no per-row bit walking, no warp scan, no divergence.
 //  * warp-granular stream-K: the blocks of the layer are dealt out in contiguous, equal (+-1) runs to the
-//    warps of a fixed grid (2 CTAs per SM), so every SM gets the same number of blocks whatever N and K are.
+//    warps of a fixed grid (3 CTAs per SM), so every SM gets the same number of blocks whatever N and K are.
 //    A warp's run covers at most two partial row groups (head / tail) plus whole ones; partials are reduced
 //    across the warps of the CTA in shared memory, and across CTAs through a small global workspace with one
 //    arrival counter per row group -- slots are summed in CTA order by the last arriver, so the result is
@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     // ---- activation loads: lane -> (token = lane>>2, 16-column segment = lane&3) of the 8 x 64 block ----------
     const uint32_t xtok = lane >> 2, xseg = lane & 3u;
     const bool x_fast = ((p.ldx & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15u) == 0) && ((p.K & 63) == 0);
+    const bool x_fast256 = x_fast && ((p.ldx & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 31u) == 0);   // one 32 B load
     const bool x_tok_ok = (m0 + (int)xtok) < p.M;
     // byte offset of (my token row, my 16-column segment, k-block 0); 32-bit (checked by the launcher) and opaque to the
     // compiler so it stays in a register instead of being recomputed every block
@@ -206,7 +207,11 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     // fast path (x_fast: 16 B aligned rows, K a multiple of 64): two unconditional 16 B loads -- rows past M read token
     // m0's row, whose products land in output columns that are never stored.  Anything else: bounds-checked elements.
     auto load_x = [&](uint32_t kblk, uint4& xa, uint4& xb) {
-        if (x_fast) {
+        if (x_fast256) {                               // sm_100 256-bit load: half the L1 wavefronts of two 128-bit loads
+            asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(xa.x), "=r"(xa.y), "=r"(xa.z), "=r"(xa.w), "=r"(xb.x), "=r"(xb.y), "=r"(xb.z), "=r"(xb.w)
+                         : "l"(xbytes + xoff));
+        } else if (x_fast) {
             const uint4* p4 = reinterpret_cast<const uint4*>(xbytes + xoff);
             xa = __ldg(p4);
             xb = __ldg(p4 + 1);
@@ -525,7 +530,7 @@ static int dk_ctas_per_sm() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("PBL_DK_CTAS");
-        v = (e && *e) ? atoi(e) : 2;
+        v = (e && *e) ? atoi(e) : 3;                  // measured on B200: 3 CTAs (24 warps) per SM is the fastest grid
         if (v < 1) v = 1;
         if (v > 4) v = 4;
     }

@@ -720,3 +720,20 @@ def test_decode_index_entry_order_spreads_banks():
                 waves += np.bincount(words % 32).max()
                 stores += 1
     assert stores > 0 and waves / stores < 2.4, waves / stores
+
+
+def test_decode_kernel_activation_alignment_paths():
+    """The three activation-load paths of the decode kernel: one 32 B load (32 B aligned rows), two 16 B loads
+    (16 B aligned only) and bounds-checked elements (anything else), through strided views of one buffer."""
+    N, K, M = 256, 512, 8
+    w, low = synth_wsim(N, K, -1, torch.float16, seed=21)
+    p = pb.PackedLinear.from_dense(t(w, torch.float16), None, t(low))
+    buf = t(rounded(make_x(77, (M, K + 64)), torch.float16), torch.float16)
+    for off in (0, 16, 8, 24, 1, 3):                      # element offsets: 0/16 -> 32 B aligned, 8/24 -> 16 B, 1/3 -> 2 B
+        xv = buf[:, off:off + K]
+        assert xv.data_ptr() % 2 == 0 and xv.stride(0) == K + 64
+        y = p.forward(xv)
+        assert p.select_kernel(M) == 4
+        ref = orc.linear(xv.float().cpu().numpy(), w)
+        assert relmax(y, ref) <= 1e-3, off
+        assert torch.equal(y, p.forward(xv.contiguous())), off       # same bits whatever the load path
