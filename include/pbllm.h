@@ -159,9 +159,8 @@ PBL_API int pbl_layer_attach_decode_index(pbl_layer* layer, const void* dsign, c
 
 /* pbl_linear_forward with a caller-owned device workspace for the decode kernel's cross-CTA reduction:
  * >= pbl_decode_workspace_bytes(layer, M) bytes, 16 B aligned, ZERO-INITIALISED ONCE by the caller (the kernel
- * leaves its arrival counters at zero), used by one stream at a time; it may be shared by all layers of a
- * device.  Calls that do not take the decode kernel ignore it.  Without a workspace (pbl_linear_forward) the
- * decode kernel takes a transient one from the stream-ordered pool and zeroes its counters on every call. */
+ * leaves it all zero again), used by one stream at a time; it may be shared by all layers of a device.  Calls that do not take the decode kernel ignore it.  Without a workspace (pbl_linear_forward) the
+ * decode kernel takes a transient one from the stream-ordered pool and zeroes it on every call. */
 PBL_API size_t pbl_decode_workspace_bytes(const pbl_layer* layer, int64_t M);
 PBL_API int pbl_linear_forward_ws(const pbl_layer* layer, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M,
                                   void* workspace, size_t workspace_bytes, void* stream);

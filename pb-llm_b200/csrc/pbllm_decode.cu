@@ -16,9 +16,9 @@
 //  * warp-granular stream-K: the blocks of the layer are dealt out in contiguous, equal (+-1) runs to the
 //    warps of a fixed grid (3 CTAs per SM), so every SM gets the same number of blocks whatever N and K are.
 //    A warp's run covers at most two partial row groups (head / tail) plus whole ones; partials are reduced
-//    across the warps of the CTA in shared memory, and across CTAs through a small global workspace with one
-//    arrival counter per row group -- slots are summed in CTA order by the last arriver, so the result is
-//    deterministic.
+//    across the warps of the CTA in shared memory, and across CTAs through a small global workspace: each
+//    contributor parks {partial, valid tag} with one 64-bit store per output (no fence, no counter), the last
+//    contributor polls the slots and sums them in CTA order, so the result is deterministic.
 //  * every weight-side load of a warp's first blocks is issued before griddepcontrol.wait: under programmatic
 //    dependent launch the packed stream of layer i+1 is in flight while layer i still computes.
 #include <cstdlib>
@@ -37,7 +37,6 @@ constexpr int kHeadBytes = kRgRows * kTok * 4;        // 1024: the warp's head-s
 constexpr int kWarpBytes = kTileBytes + kHeadBytes;   // 5120
 constexpr int kOut = kRgRows * kTok;          // 256 outputs per (row group, token pass) == kThreads
 static_assert(kOut == kThreads, "one thread per output in the cross-warp reduction");
-constexpr uint32_t kCntCap = 16384;           // arrival counters at the head of the workspace (u32 each)
 
 struct Params {
     const uint2* dsign;
@@ -48,8 +47,7 @@ struct Params {
     const void* x;
     void* y;
     int64_t ldx, ldy;
-    float* ws_part;       // [token pass][row group][slots][256] fp32 partials
-    uint32_t* ws_cnt;     // [token pass][row group] arrival counters, zero between kernels
+    void* ws_part;        // [token pass][row group][slots][256] x {fp32 partial, valid tag}: all zero between kernels
     int M, N, K;
     uint32_t tiles_c, groups, tiles_per_group;
     uint32_t nblocks;     // row groups * tiles_c
@@ -120,9 +118,9 @@ template <typename T, int kOcc>
 __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk::Params p) {
     using namespace dk;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint32_t s_wlo[kWarps], s_whi[kWarps], s_wrg[kWarps];
+    __shared__ uint32_t s_hrg[kWarps], s_trg[kWarps];   // row group of each warp's head / tail partial (or kNone)
     __shared__ uint32_t s_meta[8];                // {rg_a, rg_b, head split?, slot, expected, tail split?, slot, expected}
-    __shared__ uint32_t s_last[2];
+    constexpr uint32_t kNone = 0xffffffffu;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     uint8_t* wsm = smem + wid * kWarpBytes;
     const uint32_t tile_s = smem_u32(wsm);
@@ -157,7 +155,7 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     float2 af = make_float2(0.f, 0.f);
     if (w_lo < w_hi) af = __ldg(p.affine + (size_t)(rg * kRgRows + lane) * p.groups + cur_g);
 
-    if (lane == 0) { s_wlo[wid] = w_lo; s_whi[wid] = w_hi; s_wrg[wid] = rg_first; }
+    if (lane == 0) { s_hrg[wid] = kNone; s_trg[wid] = kNone; }
     if (tid == 0) {                               // which of this CTA's row groups are shared with other CTAs, and how
         const uint32_t rg_a = c_lo / TC, rg_b = (c_hi - 1u) / TC;
         auto owner = [&](uint32_t b) {            // CTA whose run contains block b
@@ -342,9 +340,11 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
                 }
             } else if (rg == rg_first) {
                 store_frag(head_red);                            // head partial: its own buffer, the warp may go on
+                if (lane == 0) s_hrg[wid] = rg;
             } else {
                 __syncwarp();
                 store_frag(tail_red);                            // tail partial: last thing this warp does
+                if (lane == 0) s_trg[wid] = rg;
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[0][i] = acc[1][i] = 0.f;
@@ -369,23 +369,21 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     const uint32_t om = tid >> 5, orr = tid & 31u;          // this thread's output: token om, row orr of the row group
     T* yout = reinterpret_cast<T*>(p.y) + (int64_t)(m0 + om) * p.ldy;
     const bool tok_ok = (m0 + (int)om) < p.M;
+    uint32_t hrg[kWarps], trg[kWarps];
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) { hrg[w] = s_hrg[w]; trg[w] = s_trg[w]; }
     float v_split[2] = {0.f, 0.f};                          // [0] head row group, [1] tail row group (when shared)
     for (uint32_t r = rg_a; r <= rg_b; ++r) {
-        const uint32_t r_lo = r * TC, r_hi = r_lo + TC;
-        const uint32_t seg_lo = max(c_lo, r_lo), seg_hi = min(c_hi, r_hi);
         float v = 0.f;
-        bool any = false, single_whole = false;
+        bool any = false;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            const uint32_t wl = s_wlo[w], wh = s_whi[w];
-            if (wl < wh && wl < seg_hi && wh > seg_lo) {
-                if (wl <= r_lo && wh >= r_hi) { single_whole = true; continue; }   // that warp stored the row group itself
-                any = true;
-                v += reinterpret_cast<const float*>(smem + w * kWarpBytes + ((s_wrg[w] == r) ? kTileBytes : 0))[tid];
-            }
+        for (int w = 0; w < kWarps; ++w) {                   // fixed order: warp 0's partial first
+            if (hrg[w] == r) { v += reinterpret_cast<const float*>(smem + w * kWarpBytes + kTileBytes)[tid]; any = true; }
+            if (trg[w] == r) { v += reinterpret_cast<const float*>(smem + w * kWarpBytes)[tid]; any = true; }
         }
-        if (single_whole || !any) continue;
-        if (seg_lo == r_lo && seg_hi == r_hi) {              // the whole row group lives in this CTA
+        if (!any) continue;                                  // stored by the single warp that owned it
+        const bool split = (r == rg_a && s_meta[2]) || (r == rg_b && s_meta[5]);
+        if (!split) {                                        // the whole row group lives in this CTA
             const int orow = (int)(r * kRgRows + orr);
             if (tok_ok && orow < p.N) yout[orow] = from_f32<T>((p.bias ? p.bias[orow] : 0.f) + v);
         } else if (r == rg_a) {
@@ -396,30 +394,34 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     }
     const bool hs = s_meta[2] != 0u, ts = s_meta[5] != 0u;
     if (!hs && !ts) return;
-    // shared row groups: park the partial in this CTA's slot; the last arriver sums the slots in CTA order (deterministic)
-    float* part_h = p.ws_part + (((size_t)blockIdx.y * p.rgs + rg_a) * p.slots) * kOut;
-    float* part_t = p.ws_part + (((size_t)blockIdx.y * p.rgs + rg_b) * p.slots) * kOut;
-    uint32_t* cnt_h = p.ws_cnt + (size_t)blockIdx.y * p.rgs + rg_a;
-    uint32_t* cnt_t = p.ws_cnt + (size_t)blockIdx.y * p.rgs + rg_b;
-    if (hs) part_h[(size_t)s_meta[3] * kOut + tid] = v_split[0];
-    if (ts) part_t[(size_t)s_meta[6] * kOut + tid] = v_split[1];
-    __syncthreads();                                         // every partial of this CTA is written ...
-    if (tid < 2u && (tid == 0u ? hs : ts)) {                 // ... and published by one acq_rel arrival per row group
-        uint32_t old;
-        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(tid == 0u ? cnt_h : cnt_t) : "memory");
-        s_last[tid] = (old + 1u == s_meta[tid == 0u ? 4 : 7]) ? 1u : 0u;
-    }
-    __syncthreads();
+    // Row groups shared with other CTAs.  Every contributor but the last parks its partial in its own slot as ONE 64-bit
+    // store {value, valid tag}: data and flag travel together, so there is no fence, no counter and no barrier.  The
+    // last contributor (highest CTA index, so everything it waits for was scheduled before it) polls the slots, sums them
+    // in CTA order (deterministic), clears them for the next kernel, and writes y.
+    unsigned long long* ws = reinterpret_cast<unsigned long long*>(p.ws_part);
 #pragma unroll
-    for (int f = 0; f < 2; ++f) {
-        if (!(f == 0 ? hs : ts) || !s_last[f]) continue;
-        const uint32_t r = f == 0 ? rg_a : rg_b, expected = s_meta[f == 0 ? 4 : 7];
-        const float* part = f == 0 ? part_h : part_t;
-        const int orow = (int)(r * kRgRows + orr);
-        float s = (p.bias && orow < p.N) ? p.bias[orow] : 0.f;
-        for (uint32_t k = 0; k < expected; ++k) s += __ldcg(part + (size_t)k * kOut + tid);
-        if (tok_ok && orow < p.N) yout[orow] = from_f32<T>(s);
-        if (tid == 0) *(f == 0 ? cnt_h : cnt_t) = 0u;        // ready for the next kernel that uses this workspace
+    for (int f = 1; f >= 0; --f) {                           // the tail group first: this CTA is never its last contributor
+        if (!(f == 0 ? hs : ts)) continue;
+        const uint32_t r = f == 0 ? rg_a : rg_b, slot = s_meta[f == 0 ? 3 : 6], expected = s_meta[f == 0 ? 4 : 7];
+        unsigned long long* part = ws + (((size_t)blockIdx.y * p.rgs + r) * p.slots) * kOut + tid;
+        const float v = v_split[f];
+        if (slot + 1u < expected) {
+            const unsigned long long u = (1ull << 32) | (unsigned long long)__float_as_uint(v);
+            asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(part + (size_t)slot * kOut), "l"(u) : "memory");
+        } else {
+            const int orow = (int)(r * kRgRows + orr);
+            float sum = (p.bias && orow < p.N) ? p.bias[orow] : 0.f;
+            for (uint32_t k = 0; k + 1u < expected; ++k) {
+                unsigned long long u;
+                do {
+                    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(u) : "l"(part + (size_t)k * kOut) : "memory");
+                } while ((u >> 32) == 0ull);
+                sum += __uint_as_float((uint32_t)u);
+                asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(part + (size_t)k * kOut), "l"(0ull) : "memory");
+            }
+            sum += v;
+            if (tok_ok && orow < p.N) yout[orow] = from_f32<T>(sum);
+        }
     }
 }
 
@@ -532,7 +534,7 @@ static int dk_ctas_per_sm() {
         const char* e = getenv("PBL_DK_CTAS");
         v = (e && *e) ? atoi(e) : 3;                  // measured on B200: 3 CTAs (24 warps) per SM is the fastest grid
         if (v < 1) v = 1;
-        if (v > 4) v = 4;
+        if (v > 16) v = 16;
     }
     return v;
 }
@@ -570,7 +572,7 @@ static DecodeGeom decode_geom(const Layer& L, int64_t M) {
     // a CTA's run is at least 8*q blocks long, so a row group (tiles_c blocks) meets at most this many CTAs
     g.slots = g.q ? ((uint32_t)L.tiles_c + 8u * g.q - 1u) / (8u * g.q) + 1u : 2u;
     g.passes = (uint32_t)((M + dk::kTok - 1) / dk::kTok);
-    g.ws_bytes = (size_t)dk::kCntCap * 4u + (size_t)g.passes * g.rgs * g.slots * dk::kOut * 4u;
+    g.ws_bytes = (size_t)g.passes * g.rgs * g.slots * dk::kOut * 8u;
     return g;
 }
 
@@ -579,8 +581,7 @@ bool decode_supported(const Layer& L, int64_t ldx, int64_t M) {
     if (L.dtype != PBL_F16 && L.dtype != PBL_BF16) return false;
     if (M <= 0 || M > 64) return false;
     if (ldx <= 0 || (uint64_t)M * (uint64_t)ldx * 2u >= (1ull << 31)) return false;   // 32-bit activation offsets
-    const DecodeGeom g = decode_geom(L, M);
-    return (uint64_t)g.passes * g.rgs <= dk::kCntCap;
+    return true;
 }
 
 size_t decode_workspace_bytes(const Layer& L, int64_t M) {
@@ -605,8 +606,7 @@ static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, 
     dk::Params p;
     p.dsign = L.dsign; p.eptr = L.eptr; p.ent = reinterpret_cast<const uint4*>(L.ent);
     p.affine = L.affine; p.bias = L.bias; p.x = x; p.y = y; p.ldx = ldx; p.ldy = ldy;
-    p.ws_cnt = reinterpret_cast<uint32_t*>(ws);
-    p.ws_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + (size_t)dk::kCntCap * 4u);
+    p.ws_part = ws;
     p.M = (int)M; p.N = (int)L.N; p.K = (int)L.K;
     p.tiles_c = (uint32_t)L.tiles_c; p.groups = (uint32_t)L.groups; p.tiles_per_group = (uint32_t)L.tiles_per_group;
     p.nblocks = g.nblocks; p.rgs = g.rgs; p.slots = g.slots; p.q = g.q; p.rem = g.rem;
@@ -628,7 +628,7 @@ static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, 
     return check_cuda(le, "decode launch");
 }
 
-// ws == nullptr: take a transient workspace from the stream-ordered pool and zero its counters (slower: the memset
+// ws == nullptr: take a transient workspace from the stream-ordered pool and zero it (slower: the memset
 // sits between consecutive decode kernels); callers on the hot path pass a persistent zero-initialised workspace.
 int launch_decode(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws, size_t ws_bytes,
                   cudaStream_t s) {
@@ -640,7 +640,7 @@ int launch_decode(const Layer& L, const void* x, int64_t ldx, void* y, int64_t l
     } else {
         int rc = check_cuda(cudaMallocAsync(&own, g.ws_bytes, s), "cudaMallocAsync(decode workspace)");
         if (rc) return rc;
-        rc = check_cuda(cudaMemsetAsync(own, 0, (size_t)g.passes * g.rgs * 4u, s), "cudaMemsetAsync(decode counters)");
+        rc = check_cuda(cudaMemsetAsync(own, 0, g.ws_bytes, s), "cudaMemsetAsync(decode workspace)");
         if (rc) { cudaFreeAsync(own, s); return rc; }
         ws = own;
     }
