@@ -165,6 +165,11 @@ PBL_API size_t pbl_decode_workspace_bytes(const pbl_layer* layer, int64_t M);
 PBL_API int pbl_linear_forward_ws(const pbl_layer* layer, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M,
                                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* Profiling aid for the decode kernel (tools/decode_trace.py): with a device buffer registered, the following decode
+ * launches write per-warp %globaltimer stamps (start, before/after the dependency wait, loop end, after the CTA barrier,
+ * after the cross-warp reduction, end; SM id) -- launch i at byte offset i * 16*148*8*8*8.  NULL switches it off. */
+PBL_API void pbl_decode_set_trace(void* device_buf, size_t bytes);
+
 /* XNOR-popcount forward of BiRealLinear (quant/quantizer.py:151-169): activations are binarized too,
  *   y[m][i] = sum_j sign(x[m][j]) * w_sim[i][j]        (fp32 out, NO bias -- the reference drops it, :168)
  * evaluated as hi*(popc(b&xp)-popc(b&xn)) + lo*(popc(nb&xp)-popc(nb&xn)) over the packed sign plane.

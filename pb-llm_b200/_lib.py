@@ -48,6 +48,7 @@ SYMBOLS = {
     "pbl_decode_index_fill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pbl_layer_attach_decode_index": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pbl_decode_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64]),
+    "pbl_decode_set_trace": (None, [C.c_void_p, C.c_size_t]),
     "pbl_forward_host_workspace": (C.c_size_t, [C.c_void_p, C.c_int64]),
     "pbl_linear_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pbl_bireal_workspace": (C.c_size_t, [C.c_void_p, C.c_int64]),

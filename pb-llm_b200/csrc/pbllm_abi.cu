@@ -285,6 +285,8 @@ int pbl_layer_attach_decode_index(pbl_layer* layer, const void* dsign, const voi
     return PBL_OK;
 }
 
+void pbl_decode_set_trace(void* device_buf, size_t bytes) { decode_set_trace(device_buf, bytes); }
+
 size_t pbl_decode_workspace_bytes(const pbl_layer* layer, int64_t M) {
     if (!layer || M <= 0) return 0;
     return decode_workspace_bytes(*reinterpret_cast<const Layer*>(layer), M);

@@ -74,6 +74,7 @@ int launch_decode_index_count(const Layer& L, uint32_t* eptr, cudaStream_t s);
 int launch_decode_index_fill(const Layer& L, const uint32_t* eptr, uint2* dsign, uint32_t* ent, cudaStream_t s);
 bool decode_supported(const Layer& L, int64_t ldx, int64_t M);
 size_t decode_workspace_bytes(const Layer& L, int64_t M);
+void decode_set_trace(void* buf, size_t bytes);
 int launch_decode(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws, size_t ws_bytes,
                   cudaStream_t s);
 size_t bireal_workspace_bytes(const Layer& L, int64_t M);

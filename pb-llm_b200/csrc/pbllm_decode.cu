@@ -54,6 +54,7 @@ struct Params {
     uint32_t rgs;
     uint32_t slots;       // partial slots per row group
     uint32_t q, rem;      // blocks per warp: nblocks / (grid * 8) and the remainder (the first `rem` warps take one more)
+    unsigned long long* trace;   // kTrace builds only: [cta][warp][8] globaltimer stamps of this launch
 };
 }  // namespace dk
 
@@ -88,20 +89,22 @@ __device__ __forceinline__ void dk_ldsm4(uint32_t addr, uint32_t& r0, uint32_t& 
 // 64 sign bits of one weight row -> 64 exact {lo,hi} 16-bit values, 8 STS.128: PRMT byte-sign replicate + LOP3 select
 // as in expand_row; `brow` already carries (row & 7) << 4, so chunk pc is at brow ^ (pc << 4).
 __device__ __forceinline__ void dk_expand_dense(const uint2 sg, const uint32_t LL, const uint32_t DD, const uint32_t brow) {
-    uint32_t X[2][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { X[0][k] = sg.x << k; X[1][k] = sg.y << k; }
+    for (int jq = 0; jq < 4; ++jq) {                    // bit 2pc (+16 for odd t) of a sign word = byte pc>>2 (+2), bit 2*(pc&3)
+        const int j = 2 * jq;
+        const uint32_t xa0 = sg.x << (7 - j), xb0 = sg.x << (6 - j), xa1 = sg.y << (7 - j), xb1 = sg.y << (6 - j);
 #pragma unroll
-    for (int pc = 0; pc < 8; ++pc) {
-        const int j = 2 * (pc & 3), by0 = pc >> 2;      // bit 2pc (+16 for odd t) of the sign word: byte by0 (+2), bit j
-        uint32_t h[4];
+        for (int by0 = 0; by0 < 2; ++by0) {
+            const int pc = jq + 4 * by0;
+            uint32_t h[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const uint32_t by = (uint32_t)(by0 + 2 * (t & 1));
-            const uint32_t sel = 0x8888u | by | (by << 4) | ((4u + by) << 8) | ((4u + by) << 12);
-            h[t] = sel_xor_and(LL, DD, prmt(X[t >> 1][7 - j], X[t >> 1][6 - j], sel));
+            for (int t = 0; t < 4; ++t) {
+                const uint32_t by = (uint32_t)(by0 + 2 * (t & 1));
+                const uint32_t sel = 0x8888u | by | (by << 4) | ((4u + by) << 8) | ((4u + by) << 12);
+                h[t] = sel_xor_and(LL, DD, (t >> 1) ? prmt(xa1, xb1, sel) : prmt(xa0, xb0, sel));
+            }
+            sts_v4(brow ^ ((uint32_t)pc << 4), h[0], h[1], h[2], h[3]);
         }
-        sts_v4(brow ^ ((uint32_t)pc << 4), h[0], h[1], h[2], h[3]);
     }
 }
 
@@ -114,9 +117,17 @@ __device__ __forceinline__ void dk_patch4(const uint32_t tile_s, const uint4 e) 
 }
 
 // kOcc = CTAs per SM the register budget is sized for: 3 -> 85 registers, 4 -> 64
-template <typename T, int kOcc>
+__device__ __forceinline__ unsigned long long dk_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <typename T, int kOcc, bool kTrace = false>
 __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk::Params p) {
     using namespace dk;
+    unsigned long long tr[8];
+    if (kTrace) { tr[0] = dk_now(); }
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_hrg[kWarps], s_trg[kWarps];   // row group of each warp's head / tail partial (or kNone)
     __shared__ uint32_t s_meta[8];                // {rg_a, rg_b, head split?, slot, expected, tail split?, slot, expected}
@@ -172,18 +183,23 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     }
 
     uint32_t ci = 0;                               // index of the current block in the eptr register chunk
-    uint32_t eb = __shfl_sync(0xffffffffu, epr, 0), n4 = __shfl_sync(0xffffffffu, epr, 1) - eb;
-    uint4 ea = make_uint4(0, 0, 0, 0), ec = make_uint4(0, 0, 0, 0);
     // the first min(n4, 64) units of a block sit in two register sets of h1 = ceil/2 and the rest: unit `lane` and unit
     // `h1 + lane` (the index builder deals entries to units so that each of the 8 patch stores is bank-conflict free)
-    uint32_t n1 = min(n4, 64u), h1 = (n1 + 1u) >> 1;
-    if (w_lo < w_hi) {
-        const uint4* e = p.ent + (eb + lane);
-        if (lane < h1) ea = __ldg(e);
-        if (lane + h1 < n1) ec = __ldg(e + h1);
-    } else {
-        n4 = n1 = h1 = 0;
-    }
+    struct Ent { uint4 a, c; uint32_t eb, n4; };        // one block's entries: units `lane` and `h1 + lane`, offset, unit count
+    auto ent_load = [&](Ent& E, uint32_t i) {           // i = index of the block in this warp's eptr register chunk
+        E.eb = __shfl_sync(0xffffffffu, epr, i);
+        E.n4 = __shfl_sync(0xffffffffu, epr, i + 1u) - E.eb;
+        const uint32_t n1 = min(E.n4, 64u), h1 = (n1 + 1u) >> 1;
+        const uint4* e = p.ent + (E.eb + lane);
+        asm volatile("" : "+l"(e));                     // one address computation for both predicated loads
+        if (lane < h1) E.a = __ldg(e);
+        if (lane + h1 < n1) E.c = __ldg(e + h1);
+    };
+    Ent E0, E1;                                         // two blocks of entries in flight: each set is reloaded for the block
+    E0.a = E0.c = E1.a = E1.c = make_uint4(0, 0, 0, 0); // after next right after its patch -- two blocks of cover
+    E0.eb = E0.n4 = E1.eb = E1.n4 = 0;
+    if (w_lo < w_hi) ent_load(E0, 0);
+    if (w_lo + 1u < w_hi) ent_load(E1, 1);
     uint32_t LL, DD;
     {
         const uint32_t lo = bits16<T>(af.x), hi = bits16<T>(af.y);
@@ -262,13 +278,15 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     };
 
     // activations (and y, and the workspace) belong to the stream's earlier kernels: wait before the first touch
+    if (kTrace) tr[1] = dk_now();
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (kTrace) tr[2] = dk_now();
     uint4 xa = make_uint4(0, 0, 0, 0), xb = make_uint4(0, 0, 0, 0);
     if (w_lo < w_hi) load_x(kb, xa, xb);
 
-    // Every stream is prefetched IN PLACE: a register set is reloaded for the next block right after its last use,
-    // which gives each load about one block of cover without a second register set or rotation moves.
-    for (uint32_t blk = w_lo; blk < w_hi; ++blk) {
+    // Every stream is prefetched IN PLACE: a register set is reloaded right after its last use (sign words, activations:
+    // one block of cover; salient entries, the stream that comes from DRAM with a dependent address: two sets, two blocks).
+    auto do_block = [&](const uint32_t blk, Ent& E) {
         const bool more = blk + 1 < w_hi;
         if (grouped) {
             const uint32_t g = kb / p.tiles_per_group;
@@ -286,22 +304,19 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
         sgp += more ? kRgRows : 0;                      // unconditional reload (the last block re-reads itself): the load
         sg = __ldg(sgp);                                // must land in `sg` directly, not in a temporary that is moved at once
         __syncwarp();                                   // dense rows land before other lanes patch them
-        if (lane < h1) dk_patch4(tile_s, ea);
-        if (lane + h1 < n1) dk_patch4(tile_s, ec);
-        for (uint32_t i = 64u + lane; i < n4; i += 32u) dk_patch4(tile_s, __ldg(p.ent + (eb + i)));   // rare: > 256 salient in a block
-        if (more) {
-            if (++ci == 31u) {                          // rare: refill the eptr registers (runs longer than 31 blocks)
-                ci = 0;
+        {
+            const uint32_t n1 = min(E.n4, 64u), h1 = (n1 + 1u) >> 1;
+            if (lane < h1) dk_patch4(tile_s, E.a);
+            if (lane + h1 < n1) dk_patch4(tile_s, E.c);
+            for (uint32_t i = 64u + lane; i < E.n4; i += 32u) dk_patch4(tile_s, __ldg(p.ent + (E.eb + i)));   // rare: > 256 salient in a block
+        }
+        ++ci;
+        if (blk + 2u < w_hi) {                          // this set's next block is the one after next
+            if (ci + 2u > 31u) {                        // rare: refill the eptr registers (runs longer than 30 blocks)
                 if (blk + 1u + lane <= w_hi) epr = __ldg(p.eptr + blk + 1u + lane);
+                ci = 0;
             }
-            eb = __shfl_sync(0xffffffffu, epr, ci);
-            n4 = __shfl_sync(0xffffffffu, epr, ci + 1u) - eb;
-            n1 = min(n4, 64u);
-            h1 = (n1 + 1u) >> 1;
-            const uint4* e = p.ent + (eb + lane);
-            asm volatile("" : "+l"(e));                 // one address computation for both predicated loads
-            if (lane < h1) ea = __ldg(e);
-            if (lane + h1 < n1) ec = __ldg(e + h1);
+            ent_load(E, ci + 1u);
         }
         __syncwarp();                                   // the tile is complete and visible to the whole warp
 
@@ -360,10 +375,16 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
                 }
             }
         }
+    };
+    for (uint32_t blk = w_lo; blk < w_hi; blk += 2u) {   // unrolled by two: the entry sets alternate without register moves
+        do_block(blk, E0);
+        if (blk + 1u < w_hi) do_block(blk + 1u, E1);
     }
 
     // ---- cross-warp reduction in shared memory; row groups shared with other CTAs go through the workspace ----------
+    if (kTrace) tr[3] = dk_now();
     __syncthreads();
+    if (kTrace) tr[4] = dk_now();
     if (c_lo >= c_hi) return;
     const uint32_t rg_a = s_meta[0], rg_b = s_meta[1];
     const uint32_t om = tid >> 5, orr = tid & 31u;          // this thread's output: token om, row orr of the row group
@@ -393,7 +414,18 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
         }
     }
     const bool hs = s_meta[2] != 0u, ts = s_meta[5] != 0u;
-    if (!hs && !ts) return;
+    if (kTrace) tr[5] = dk_now();
+    auto trace_out = [&]() {
+        if (kTrace && lane == 0) {
+            tr[6] = dk_now();
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            tr[7] = ((unsigned long long)smid << 32) | (w_hi - w_lo);
+            unsigned long long* o = p.trace + ((size_t)blockIdx.x * kWarps + wid) * 8u;
+            for (int i = 0; i < 8; ++i) o[i] = tr[i];
+        }
+    };
+    if (!hs && !ts) { trace_out(); return; }
     // Row groups shared with other CTAs.  Every contributor but the last parks its partial in its own slot as ONE 64-bit
     // store {value, valid tag}: data and flag travel together, so there is no fence, no counter and no barrier.  The
     // last contributor (highest CTA index, so everything it waits for was scheduled before it) polls the slots, sums them
@@ -423,6 +455,7 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
             if (tok_ok && orow < p.N) yout[orow] = from_f32<T>(sum);
         }
     }
+    trace_out();
 }
 
 // ---- decode index construction (one-time, from the packed form) ---------------------------------------------------
@@ -558,6 +591,17 @@ static int dk_num_sms() {
     return sms[dev] > 0 ? sms[dev] : 148;
 }
 
+// profiling aid (tools/decode_trace.py): when a device buffer is registered, launches go through the kTrace build and
+// launch i writes its per-warp globaltimer stamps at trace + i * kTraceStride
+static unsigned long long* g_trace = nullptr;
+static size_t g_trace_launches = 0, g_trace_next = 0;
+constexpr size_t kTraceStride = 16u * 148u * dk::kWarps * 8u;     // u64 per launch (grid <= 16 CTAs per SM)
+void decode_set_trace(void* buf, size_t bytes) {
+    g_trace = reinterpret_cast<unsigned long long*>(buf);
+    g_trace_launches = buf ? bytes / (kTraceStride * 8u) : 0;
+    g_trace_next = 0;
+}
+
 struct DecodeGeom { uint32_t nblocks, rgs, grid, slots, passes, q, rem; size_t ws_bytes; };
 
 static DecodeGeom decode_geom(const Layer& L, int64_t M) {
@@ -623,7 +667,16 @@ static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, 
     if (pdl < 0) { const char* e = getenv("PBL_PDL"); pdl = (e && *e) ? atoi(e) : 1; }
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, decode_mma_kernel<T, kOcc>, p);
+    cudaError_t le;
+    if (g_trace && g_trace_next < g_trace_launches && kOcc == 3) {
+        p.trace = g_trace + (g_trace_next++) * kTraceStride;
+        static bool tattr = false;
+        if (!tattr) { cudaFuncSetAttribute(decode_mma_kernel<T, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); tattr = true; }
+        le = cudaLaunchKernelEx(&cfg, decode_mma_kernel<T, 3, true>, p);
+    } else {
+        p.trace = nullptr;
+        le = cudaLaunchKernelEx(&cfg, decode_mma_kernel<T, kOcc>, p);
+    }
     count_launch();
     return check_cuda(le, "decode launch");
 }
