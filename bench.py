@@ -427,7 +427,12 @@ def main():
                   "kernel": {4: "pbl decode kernel (positioned salient entries, warp-granular stream-K, mma.sync)",
                              2: "pbl mma.sync bit-plane skinny kernel"}.get(layers[0][0].select_kernel(Md), "pbl CUDA-core bit-plane kernel"),
                   "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                               "traffic": None, "algorithmic_bytes_per_step": b_bin + b_sal,
+                               # dram__bytes_read+write per launch from the committed ncu --set full capture of the same
+                               # launches (profiles/r01_decode_kernel_M8_llama7b_shapes.md): 9.24 MB (4096x4096), 24.53 MB
+                               # (11008x4096), 24.35 MB (4096x11008) -> average over the 7 linears of a decoder layer
+                               "traffic": ((4 * 9.2352e6 + 2 * 24.526848e6 + 24.348672e6) / 7.0) if (layers[0][0].select_kernel(Md) == 4 and Md == 8 and args.low_frac == 0.9) else None,
+                               "algorithmic_bytes_per_launch": (b_bin + b_sal) / max(1, sum(len(r) for r in layers)),
+                               "algorithmic_bytes_per_step": b_bin + b_sal,
                                "actual_packed_bytes": packed_bytes, "decode_index_bytes": dindex_bytes,
                                "actual_bytes_gbs": (dindex_bytes if layers[0][0].select_kernel(Md) == 4 else packed_bytes) / (ms_d * 1e-3) / 1e9,
                                "peak_source": pk["src"]}}

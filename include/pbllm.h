@@ -165,6 +165,12 @@ PBL_API size_t pbl_decode_workspace_bytes(const pbl_layer* layer, int64_t M);
 PBL_API int pbl_linear_forward_ws(const pbl_layer* layer, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M,
                                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* Host-only: the decode kernel's launch plan for an N x K layer, M tokens, on a device with `sms` SMs and
+ * `ctas_per_sm` CTAs of 8 warps per SM.  out8 = {blocks, row groups, grid.x, token passes, q, rem, slots, workspace KiB}:
+ * warp g of the grid owns blocks [g*q + min(g, rem), (g+1)*q + min(g+1, rem)) of the row-group-major block order, and a
+ * row group's partials need at most `slots` workspace slots (tests/test_decode_plan.py checks both on the CPU). */
+PBL_API int pbl_decode_plan(int64_t N, int64_t K, int64_t M, int sms, int ctas_per_sm, uint32_t* out8);
+
 /* Profiling aid for the decode kernel (tools/decode_trace.py): with a device buffer registered, the following decode
  * launches write per-warp %globaltimer stamps (start, before/after the dependency wait, loop end, after the CTA barrier,
  * after the cross-warp reduction, end; SM id) -- launch i at byte offset i * 16*148*8*8*8.  NULL switches it off. */

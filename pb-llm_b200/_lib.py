@@ -49,6 +49,7 @@ SYMBOLS = {
     "pbl_layer_attach_decode_index": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pbl_decode_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64]),
     "pbl_decode_set_trace": (None, [C.c_void_p, C.c_size_t]),
+    "pbl_decode_plan": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_uint32)]),
     "pbl_forward_host_workspace": (C.c_size_t, [C.c_void_p, C.c_int64]),
     "pbl_linear_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pbl_bireal_workspace": (C.c_size_t, [C.c_void_p, C.c_int64]),

@@ -285,6 +285,13 @@ int pbl_layer_attach_decode_index(pbl_layer* layer, const void* dsign, const voi
     return PBL_OK;
 }
 
+int pbl_decode_plan(int64_t N, int64_t K, int64_t M, int sms, int ctas_per_sm, uint32_t* out8) {
+    if (!out8) { set_error("pbl_decode_plan: out is NULL"); return PBL_ERR_NULL; }
+    if (N <= 0 || K <= 0 || M <= 0 || sms <= 0 || ctas_per_sm <= 0) { set_error("pbl_decode_plan: arguments must be positive"); return PBL_ERR_SHAPE; }
+    decode_plan(N, K, M, sms, ctas_per_sm, out8);
+    return PBL_OK;
+}
+
 void pbl_decode_set_trace(void* device_buf, size_t bytes) { decode_set_trace(device_buf, bytes); }
 
 size_t pbl_decode_workspace_bytes(const pbl_layer* layer, int64_t M) {

@@ -604,11 +604,25 @@ void decode_set_trace(void* buf, size_t bytes) {
 
 struct DecodeGeom { uint32_t nblocks, rgs, grid, slots, passes, q, rem; size_t ws_bytes; };
 
+static DecodeGeom decode_geom_raw(int64_t tiles_r, int64_t tiles_c, int64_t M, uint32_t want);
+
 static DecodeGeom decode_geom(const Layer& L, int64_t M) {
+    return decode_geom_raw(L.tiles_r, L.tiles_c, M, (uint32_t)(dk_num_sms() * dk_ctas_per_sm()));
+}
+
+// host-only: the launch plan of the decode kernel for an N x K layer on a device with `sms` SMs (pbl_decode_plan)
+void decode_plan(int64_t N, int64_t K, int64_t M, int sms, int ctas_per_sm, uint32_t out[8]) {
+    const int64_t tr = (N + kTileRows - 1) / kTileRows, tc = (K + kTileCols - 1) / kTileCols;
+    const DecodeGeom g = decode_geom_raw(tr, tc, M, (uint32_t)(sms * ctas_per_sm));
+    out[0] = g.nblocks; out[1] = g.rgs; out[2] = g.grid; out[3] = g.passes; out[4] = g.q; out[5] = g.rem; out[6] = g.slots;
+    out[7] = (uint32_t)(g.ws_bytes >> 10);
+}
+
+static DecodeGeom decode_geom_raw(int64_t tiles_r, int64_t tiles_c, int64_t M, uint32_t want) {
+    struct { int64_t tiles_r, tiles_c; } L = {tiles_r, tiles_c};
     DecodeGeom g;
     g.rgs = (uint32_t)(L.tiles_r * kRgPerTile);
     g.nblocks = g.rgs * (uint32_t)L.tiles_c;
-    const uint32_t want = (uint32_t)(dk_num_sms() * dk_ctas_per_sm());
     const uint32_t cap = g.nblocks / dk::kWarps > 0 ? g.nblocks / dk::kWarps : 1u;   // at least one block per warp
     g.grid = cap < want ? cap : want;
     g.q = g.nblocks / (g.grid * dk::kWarps);
