@@ -452,7 +452,7 @@ def main():
             blayers.append(row)
         xb_in = {k: v[:Md].contiguous() for k, v in xin.items()}
         bouts = [torch.empty(Md, p.N, device=dev, dtype=torch.float32) for p in blayers[0]]
-        bws = torch.empty(max(p.bireal_workspace_bytes(Md) for p in blayers[0]), dtype=torch.uint8, device=dev)
+        bws = torch.zeros(max(p.bireal_workspace_bytes(Md) for p in blayers[0]), dtype=torch.uint8, device=dev)   # zeroed once
 
         def bstep():
             for row in blayers:

@@ -181,10 +181,17 @@ PBL_API void pbl_decode_set_trace(void* device_buf, size_t bytes);
  * evaluated as hi*(popc(b&xp)-popc(b&xn)) + lo*(popc(nb&xp)-popc(nb&xn)) over the packed sign plane.
  * `layer` must be packed from alpha_i*sign(W) (all salient values exactly zero).  x: device [M][ldx] of
  * x_dtype (any pbl_dtype, independent of the layer's); y: device float [M][ldy]; workspace: device,
- * 16 B aligned, >= pbl_bireal_workspace(layer, M) bytes (packed activation sign planes). */
+ * 16 B aligned, >= pbl_bireal_workspace(layer, M) bytes (packed activation sign planes; plain scratch).
+ * pbl_bireal_forward_ws additionally takes a ZERO-INITIALISED reduction workspace of >= pbl_bireal_fixup_workspace(layer, M)
+ * bytes (same contract as pbl_linear_forward_ws's: left zero by every call, one stream at a time, shareable between
+ * layers and with the decode kernel); with it, pure sign layers (sign_planes given) run the stream-K XNOR kernel that
+ * balances the layer's blocks over all SMs.  Without it the row-group-per-CTA kernel runs. */
 PBL_API size_t pbl_bireal_workspace(const pbl_layer* layer, int64_t M);
 PBL_API int pbl_bireal_forward(const pbl_layer* layer, const void* x, int64_t ldx, int x_dtype, float* y, int64_t ldy,
                                int64_t M, void* workspace, void* stream);
+PBL_API size_t pbl_bireal_fixup_workspace(const pbl_layer* layer, int64_t M);
+PBL_API int pbl_bireal_forward_ws(const pbl_layer* layer, const void* x, int64_t ldx, int x_dtype, float* y, int64_t ldy,
+                                  int64_t M, void* workspace, void* fixup_workspace, size_t fixup_workspace_bytes, void* stream);
 
 /* Which kernel pbl_linear_forward would launch for this (layer, M): 0 = CUDA-core bit-plane
  * kernel (fp32 I/O), 1 = tcgen05 bit-plane GEMM (M above PBL_SKINNY_MAX_M, default 16),

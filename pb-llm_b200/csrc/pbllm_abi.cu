@@ -304,8 +304,18 @@ size_t pbl_bireal_workspace(const pbl_layer* layer, int64_t M) {
     return bireal_workspace_bytes(*reinterpret_cast<const Layer*>(layer), M);
 }
 
+size_t pbl_bireal_fixup_workspace(const pbl_layer* layer, int64_t M) {
+    if (!layer || M <= 0) return 0;
+    return bireal_fixup_workspace_bytes(*reinterpret_cast<const Layer*>(layer), M);
+}
+
 int pbl_bireal_forward(const pbl_layer* layer, const void* x, int64_t ldx, int x_dtype, float* y, int64_t ldy, int64_t M,
                        void* workspace, void* stream) {
+    return pbl_bireal_forward_ws(layer, x, ldx, x_dtype, y, ldy, M, workspace, nullptr, 0, stream);
+}
+
+int pbl_bireal_forward_ws(const pbl_layer* layer, const void* x, int64_t ldx, int x_dtype, float* y, int64_t ldy, int64_t M,
+                          void* workspace, void* fixup_ws, size_t fixup_bytes, void* stream) {
     if (!layer) { set_error("pbl_bireal_forward: null layer"); return PBL_ERR_NULL; }
     const Layer& L = *reinterpret_cast<const Layer*>(layer);
     if (M < 0 || M > 65535LL * 8) { set_error("pbl_bireal_forward: bad M=%lld", (long long)M); return PBL_ERR_SHAPE; }
@@ -316,7 +326,8 @@ int pbl_bireal_forward(const pbl_layer* layer, const void* x, int64_t ldx, int x
     if (!aligned16(workspace)) { set_error("pbl_bireal_forward: workspace must be 16 B aligned"); return PBL_ERR_ALIGN; }
     int rc = device_check_impl();
     if (rc) return rc;
-    return launch_bireal(L, x, ldx, x_dtype, y, ldy, M, workspace, (cudaStream_t)stream);
+    if (fixup_ws && (reinterpret_cast<uintptr_t>(fixup_ws) & 15u)) { set_error("pbl_bireal_forward: fixup workspace must be 16 B aligned"); return PBL_ERR_ALIGN; }
+    return launch_bireal(L, x, ldx, x_dtype, y, ldy, M, workspace, fixup_ws, fixup_bytes, (cudaStream_t)stream);
 }
 
 size_t pbl_forward_host_workspace(const pbl_layer* layer, int64_t M) {

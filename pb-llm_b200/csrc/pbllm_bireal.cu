@@ -9,6 +9,8 @@
 // salient values are all exactly zero (sign(0) = 0 weights), which pack(alpha*sign(W)) guarantees.
 // HBM-bound on the 0.25 B/weight plane stream: lane = weight row, warps split K, x bits are
 // broadcast 16 B loads.
+#include <cstdlib>
+
 #include "pbllm_common.cuh"
 
 namespace pbl {
@@ -106,14 +108,258 @@ bireal_xnor_kernel(const uint4* __restrict__ planes, const uint2* __restrict__ s
     }
 }
 
+
+// ---- stream-K XNOR-popcount kernel (pure sign layers: compact sign planes, no zero weights) -----------------------------
+// Same work partition and cross-CTA reduction as decode_mma_kernel (csrc/pbllm_decode.cu): the layer's 32x64 blocks are
+// dealt in contiguous, equal runs to the warps of a fixed grid; a warp keeps integer counts d1 (sum of sign(x) over the
+// `hi` positions of its rows) and S (sum of sign(x) over the whole block; the `lo` positions are the complement), folds
+// them with the row's {lo,hi} when its part of a row group ends, and partial row groups are reduced across the CTA's
+// warps in shared memory and across CTAs through tagged 64-bit workspace slots summed in CTA order (deterministic).
+// The activation bit planes of a warp's run are staged eight blocks at a time in its private shared memory.
+namespace bsk {
+constexpr int kWarps = 8, kThreads = 256, kTok = 8, kOut = 256;
+constexpr int kChunk = 8;                                   // blocks of activation bits staged at once
+constexpr int kXbBytes = kChunk * kTok * 16;                // 1024: uint4 {xp0, xp1, xn0, xn1} per (block, token)
+constexpr int kDxBytes = kChunk * kTok * 4;                 // 256
+constexpr int kRedBytes = 2 * kOut * 4;                     // 2048: head and tail partial of the warp
+constexpr int kWarpBytes = kXbBytes + kDxBytes + kRedBytes; // 3328
+struct Params {
+    const uint2* sign_planes;
+    const float2* affine;
+    const uint4* xb;
+    const int* dx;
+    float* y;
+    int64_t ldy;
+    unsigned long long* ws;
+    int M, N;
+    uint32_t tiles_c, groups, tiles_per_group, rgs, slots, q, rem;
+};
+}  // namespace bsk
+
+__global__ void __launch_bounds__(bsk::kThreads, 4) bireal_sk_kernel(const bsk::Params p) {
+    using namespace bsk;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint32_t s_hrg[kWarps], s_trg[kWarps];
+    __shared__ uint32_t s_meta[8];
+    constexpr uint32_t kNone = 0xffffffffu;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    uint8_t* wsm = smem + wid * kWarpBytes;
+    uint4* xs = reinterpret_cast<uint4*>(wsm);                               // [kChunk][kTok]
+    int* dxs = reinterpret_cast<int*>(wsm + kXbBytes);                       // [kChunk][kTok]
+    float* head_red = reinterpret_cast<float*>(wsm + kXbBytes + kDxBytes);   // [kTok][32]
+    float* tail_red = head_red + kOut;
+
+    const uint32_t TC = p.tiles_c, q = p.q, rem = p.rem;
+    auto wstart = [&](uint32_t gw) { return gw * q + min(gw, rem); };
+    const uint32_t gw0 = blockIdx.x * kWarps;
+    const uint32_t c_lo = wstart(gw0), c_hi = wstart(gw0 + kWarps);
+    const uint32_t w_lo = wstart(gw0 + wid), w_hi = wstart(gw0 + wid + 1u);
+    const int m0 = blockIdx.y * kTok;
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    uint32_t rg = 0, kb = 0;
+    if (w_lo < w_hi) { rg = w_lo / TC; kb = w_lo - rg * TC; }
+    const uint32_t rg_first = rg;
+    auto sign_ptr = [&](uint32_t r, uint32_t k) {            // tile-major compact planes: [tile row][k-block][128 rows]
+        return p.sign_planes + ((size_t)(r / kRgPerTile) * TC + k) * kTileRows + (r % kRgPerTile) * kRgRows + lane;
+    };
+    uint2 sg = make_uint2(0, 0);
+    if (w_lo < w_hi) sg = __ldg(sign_ptr(rg, kb));
+    const bool grouped = p.groups > 1;
+    uint32_t cur_g = grouped ? kb / p.tiles_per_group : 0u;
+    float2 af = make_float2(0.f, 0.f);
+    if (w_lo < w_hi) af = __ldg(p.affine + (size_t)(rg * kRgRows + lane) * p.groups + cur_g);
+    if (lane == 0) { s_hrg[wid] = kNone; s_trg[wid] = kNone; }
+    if (tid == 0) {
+        const uint32_t rg_a = c_lo / TC, rg_b = (c_hi - 1u) / TC;
+        auto owner = [&](uint32_t b) {
+            const uint32_t cut = rem * (q + 1u);
+            const uint32_t gw = b < cut ? b / (q + 1u) : rem + (b - cut) / q;
+            return gw / kWarps;
+        };
+        s_meta[0] = rg_a; s_meta[1] = rg_b;
+        const bool hs = c_lo > rg_a * TC || c_hi < rg_a * TC + TC;
+        const bool ts = rg_b != rg_a && c_hi < rg_b * TC + TC;
+        s_meta[2] = hs; s_meta[5] = ts;
+        if (hs) { const uint32_t f = owner(rg_a * TC); s_meta[3] = blockIdx.x - f; s_meta[4] = owner(rg_a * TC + TC - 1u) - f + 1u; }
+        if (ts) { const uint32_t f = owner(rg_b * TC); s_meta[6] = blockIdx.x - f; s_meta[7] = owner(rg_b * TC + TC - 1u) - f + 1u; }
+    }
+
+    int d1[kTok], S[kTok];
+    float acc[kTok];
+#pragma unroll
+    for (int m = 0; m < kTok; ++m) { d1[m] = S[m] = 0; acc[m] = 0.f; }
+    auto fold = [&]() {                                       // counts -> values with the current {lo,hi}
+#pragma unroll
+        for (int m = 0; m < kTok; ++m) { acc[m] += af.y * (float)d1[m] + af.x * (float)(S[m] - d1[m]); d1[m] = S[m] = 0; }
+    };
+
+    // the activation bits come from the binarize kernel just before this one in the stream
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    const uint32_t sm_tok = lane >> 2, sm_j = lane & 3u;      // staging: lane -> token, blocks j and j+4 of the chunk
+    const bool sm_ok = (m0 + (int)sm_tok) < p.M;
+    uint32_t ci = kChunk;                                     // index of the current block in the staged chunk
+    uint32_t kb_c = kb;                                       // k-block of the chunk's first block
+    for (uint32_t blk = w_lo; blk < w_hi; ++blk) {
+        const bool more = blk + 1 < w_hi;
+        if (ci == kChunk) {                                   // stage the bit planes of the next (up to) 8 blocks of the run
+            ci = 0;
+            kb_c = kb;
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t i = sm_j + 4u * h;
+                uint32_t k = kb_c + i;
+                while (k >= TC) k -= TC;                      // the run may continue in the next row group
+                uint4 v = make_uint4(0, 0, 0, 0);
+                int dv = 0;
+                if (sm_ok && blk + i < w_hi) {
+                    v = __ldg(p.xb + (size_t)(m0 + sm_tok) * TC + k);
+                    dv = __ldg(p.dx + (size_t)(m0 + sm_tok) * TC + k);
+                }
+                xs[i * kTok + sm_tok] = v;
+                dxs[i * kTok + sm_tok] = dv;
+            }
+            __syncwarp();
+        }
+        if (grouped) {
+            const uint32_t g = kb / p.tiles_per_group;
+            if (g != cur_g) {
+                fold();
+                cur_g = g;
+                af = __ldg(p.affine + (size_t)(rg * kRgRows + lane) * p.groups + g);
+            }
+        }
+        const uint2 b = sg;
+        ++kb;
+        const bool rg_end = kb == TC;
+        if (more) sg = __ldg(sign_ptr(rg_end ? rg + 1u : rg, rg_end ? 0u : kb));     // in-place prefetch of the next block
+#pragma unroll
+        for (int m = 0; m < kTok; ++m) {
+            const uint4 xv = xs[ci * kTok + m];               // same address in every lane: a broadcast
+            d1[m] += __popc(b.x & xv.x) + __popc(b.y & xv.y) - __popc(b.x & xv.z) - __popc(b.y & xv.w);
+            S[m] += dxs[ci * kTok + m];
+        }
+        ++ci;
+        if (rg_end || !more) {
+            fold();
+            const bool whole = rg_end && (w_lo <= rg * TC);
+            if (whole) {
+                const int orow = (int)(rg * kRgRows + lane);
+                if (orow < p.N) {
+#pragma unroll
+                    for (int m = 0; m < kTok; ++m)
+                        if (m0 + m < p.M) p.y[(int64_t)(m0 + m) * p.ldy + orow] = acc[m];
+                }
+            } else {
+                float* dst = (rg == rg_first) ? head_red : tail_red;
+#pragma unroll
+                for (int m = 0; m < kTok; ++m) dst[m * kRgRows + lane] = acc[m];
+                if (lane == 0) { if (rg == rg_first) s_hrg[wid] = rg; else s_trg[wid] = rg; }
+            }
+#pragma unroll
+            for (int m = 0; m < kTok; ++m) acc[m] = 0.f;
+            if (rg_end) {
+                kb = 0;
+                ++rg;
+                if (more) {
+                    cur_g = 0;
+                    af = __ldg(p.affine + (size_t)(rg * kRgRows + lane) * p.groups);
+                }
+            }
+        }
+    }
+
+    __syncthreads();
+    if (c_lo >= c_hi) return;
+    const uint32_t rg_a = s_meta[0], rg_b = s_meta[1];
+    const uint32_t om = tid >> 5, orr = tid & 31u;
+    float* yout = p.y + (int64_t)(m0 + om) * p.ldy;
+    const bool tok_ok = (m0 + (int)om) < p.M;
+    uint32_t hrg[kWarps], trg[kWarps];
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) { hrg[w] = s_hrg[w]; trg[w] = s_trg[w]; }
+    float v_split[2] = {0.f, 0.f};
+    for (uint32_t r = rg_a; r <= rg_b; ++r) {
+        float v = 0.f;
+        bool any = false;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const float* red = reinterpret_cast<const float*>(smem + w * kWarpBytes + kXbBytes + kDxBytes);
+            if (hrg[w] == r) { v += red[tid]; any = true; }
+            if (trg[w] == r) { v += red[kOut + tid]; any = true; }
+        }
+        if (!any) continue;
+        const bool split = (r == rg_a && s_meta[2]) || (r == rg_b && s_meta[5]);
+        if (!split) {
+            const int orow = (int)(r * kRgRows + orr);
+            if (tok_ok && orow < p.N) yout[orow] = v;
+        } else if (r == rg_a) {
+            v_split[0] = v;
+        } else {
+            v_split[1] = v;
+        }
+    }
+    const bool hs = s_meta[2] != 0u, ts = s_meta[5] != 0u;
+    if (!hs && !ts) return;
+#pragma unroll
+    for (int f = 1; f >= 0; --f) {
+        if (!(f == 0 ? hs : ts)) continue;
+        const uint32_t r = f == 0 ? rg_a : rg_b, slot = s_meta[f == 0 ? 3 : 6], expected = s_meta[f == 0 ? 4 : 7];
+        unsigned long long* part = p.ws + (((size_t)blockIdx.y * p.rgs + r) * p.slots) * kOut + tid;
+        const float v = v_split[f];
+        if (slot + 1u < expected) {
+            const unsigned long long u = (1ull << 32) | (unsigned long long)__float_as_uint(v);
+            asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(part + (size_t)slot * kOut), "l"(u) : "memory");
+        } else {
+            const int orow = (int)(r * kRgRows + orr);
+            float sum = 0.f;
+            for (uint32_t k = 0; k + 1u < expected; ++k) {
+                unsigned long long u;
+                do {
+                    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(u) : "l"(part + (size_t)k * kOut) : "memory");
+                } while ((u >> 32) == 0ull);
+                sum += __uint_as_float((uint32_t)u);
+                asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(part + (size_t)k * kOut), "l"(0ull) : "memory");
+            }
+            sum += v;
+            if (tok_ok && orow < p.N) yout[orow] = sum;
+        }
+    }
+}
+
+static int bireal_sk_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PBL_BIREAL_SK"); v = (e && *e) ? atoi(e) : 1; }
+    return v;
+}
+
+static size_t bireal_fixup_bytes(const Layer& L, int64_t M) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) { (void)cudaGetLastError(); sms = 148; }
+    uint32_t pl[8];
+    decode_plan(L.N, L.K, M, sms, 4, pl);
+    return (size_t)pl[3] * pl[1] * pl[6] * bsk::kOut * 8u;
+}
+
 size_t bireal_workspace_bytes(const Layer& L, int64_t M) {
     return (size_t)M * (size_t)L.tiles_c * (sizeof(uint4) + sizeof(int)) + 256;
 }
 
+// zero-initialised workspace the stream-K kernel needs for its cross-CTA reduction (same contract as the decode
+// kernel's: left zero by every call, one stream at a time); 0 when the layer does not qualify for that kernel
+size_t bireal_fixup_workspace_bytes(const Layer& L, int64_t M) {
+    if (!L.sign_planes || !bireal_sk_enabled() || M <= 0 || M > 64) return 0;   // larger M: the passes would re-read the planes
+    return bireal_fixup_bytes(L, M);
+}
 int launch_bireal(const Layer& L, const void* x, int64_t ldx, int x_dtype, float* y, int64_t ldy, int64_t M, void* workspace,
-                  cudaStream_t s) {
+                  void* fixup_ws, size_t fixup_bytes, cudaStream_t s) {
     uint4* xb = reinterpret_cast<uint4*>(workspace);
     int* dx = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + (((size_t)M * L.tiles_c * sizeof(uint4) + 255) / 256) * 256);
+    // (xb and dx fit in bireal_scratch_bytes: M*tiles_c*20 + 256 >= the 256-rounded xb region + M*tiles_c*4)
     const dim3 gb((unsigned)L.tiles_c, (unsigned)M);
     switch (x_dtype) {
         case PBL_F16: bireal_binarize_kernel<__half><<<gb, 64, 0, s>>>((const __half*)x, ldx, L.K, (int)L.tiles_c, xb, dx); break;
@@ -123,6 +369,34 @@ int launch_bireal(const Layer& L, const void* x, int64_t ldx, int x_dtype, float
     }
     int rc = check_cuda(cudaGetLastError(), "bireal binarize launch");
     if (rc) return rc;
+    if (fixup_ws && fixup_bytes >= bireal_fixup_workspace_bytes(L, M) && bireal_fixup_workspace_bytes(L, M) > 0) {
+        // pure sign layer + a zeroed reduction workspace: stream-K kernel, balanced over all SMs
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        uint32_t pl[8];
+        decode_plan(L.N, L.K, M, sms, 4, pl);
+        bsk::Params p;
+        p.sign_planes = L.sign_planes; p.affine = L.affine; p.xb = xb; p.dx = dx; p.y = y; p.ldy = ldy;
+        p.ws = reinterpret_cast<unsigned long long*>(fixup_ws);
+        p.M = (int)M; p.N = (int)L.N;
+        p.tiles_c = (uint32_t)L.tiles_c; p.groups = (uint32_t)L.groups; p.tiles_per_group = (uint32_t)L.tiles_per_group;
+        p.rgs = pl[1]; p.slots = pl[6]; p.q = pl[4]; p.rem = pl[5];
+        const int smem = bsk::kWarps * bsk::kWarpBytes;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(pl[2], pl[3]);
+        cfg.blockDim = dim3(bsk::kThreads);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, bireal_sk_kernel, p);
+        count_launch(2);
+        return check_cuda(le, "bireal stream-K launch");
+    }
     const unsigned gx = (unsigned)(L.n_pad / kRgRows);
 #define PBL_BR_LAUNCH(MT)                                                                                                      \
     do {                                                                                                                       \

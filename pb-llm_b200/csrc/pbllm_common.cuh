@@ -79,7 +79,8 @@ void decode_plan(int64_t N, int64_t K, int64_t M, int sms, int ctas_per_sm, uint
 int launch_decode(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws, size_t ws_bytes,
                   cudaStream_t s);
 size_t bireal_workspace_bytes(const Layer& L, int64_t M);
+size_t bireal_fixup_workspace_bytes(const Layer& L, int64_t M);
 int launch_bireal(const Layer& L, const void* x, int64_t ldx, int x_dtype, float* y, int64_t ldy, int64_t M, void* workspace,
-                  cudaStream_t s);
+                  void* fixup_ws, size_t fixup_bytes, cudaStream_t s);
 
 }  // namespace pbl

@@ -239,8 +239,13 @@ class PackedLinear:
             with torch.cuda.device(x.device):
                 ws = workspace if workspace is not None else \
                     torch.empty(int(lib.pbl_bireal_workspace(self.handle, M)), dtype=torch.uint8, device=x.device)
-                rc = lib.pbl_bireal_forward(self.handle, x2.data_ptr(), x2.stride(0) if M > 1 else self.K, _DT[x.dtype],
-                                            y.data_ptr(), y.stride(0), M, ws.data_ptr(), _stream(x.device))
+                st = torch.cuda.current_stream(x.device).cuda_stream
+                fix_ptr, fix_bytes = None, int(lib.pbl_bireal_fixup_workspace(self.handle, M))
+                if fix_bytes:                        # stream-K XNOR kernel: the persistent zeroed reduction workspace
+                    fws = _decode_workspace(x.device, st, fix_bytes)
+                    fix_ptr, fix_bytes = fws.data_ptr(), fws.numel()
+                rc = lib.pbl_bireal_forward_ws(self.handle, x2.data_ptr(), x2.stride(0) if M > 1 else self.K, _DT[x.dtype],
+                                               y.data_ptr(), y.stride(0), M, ws.data_ptr(), fix_ptr, fix_bytes, st)
             _lib.check(rc, "pbl_bireal_forward")
         if out is not None:
             return y
