@@ -184,8 +184,8 @@ PBL_API void pbl_decode_set_trace(void* device_buf, size_t bytes);
  * 16 B aligned, >= pbl_bireal_workspace(layer, M) bytes (packed activation sign planes; plain scratch).
  * pbl_bireal_forward_ws additionally takes a ZERO-INITIALISED reduction workspace of >= pbl_bireal_fixup_workspace(layer, M)
  * bytes (same contract as pbl_linear_forward_ws's: left zero by every call, one stream at a time, shareable between
- * layers and with the decode kernel); with it, pure sign layers (sign_planes given) run the stream-K XNOR kernel that
- * balances the layer's blocks over all SMs.  Without it the row-group-per-CTA kernel runs. */
+ * layers and with the decode kernel); with it (and M <= 64) the stream-K XNOR kernel runs, which balances the layer's
+ * blocks over all SMs.  Without it the row-group-per-CTA kernel runs. */
 PBL_API size_t pbl_bireal_workspace(const pbl_layer* layer, int64_t M);
 PBL_API int pbl_bireal_forward(const pbl_layer* layer, const void* x, int64_t ldx, int x_dtype, float* y, int64_t ldy,
                                int64_t M, void* workspace, void* stream);

@@ -109,7 +109,7 @@ bireal_xnor_kernel(const uint4* __restrict__ planes, const uint2* __restrict__ s
 }
 
 
-// ---- stream-K XNOR-popcount kernel (pure sign layers: compact sign planes, no zero weights) -----------------------------
+// ---- stream-K XNOR-popcount kernel ----------------------------------------------------------------------------------------
 // Same work partition and cross-CTA reduction as decode_mma_kernel (csrc/pbllm_decode.cu): the layer's 32x64 blocks are
 // dealt in contiguous, equal runs to the warps of a fixed grid; a warp keeps integer counts d1 (sum of sign(x) over the
 // `hi` positions of its rows) and S (sum of sign(x) over the whole block; the `lo` positions are the complement), folds
@@ -124,7 +124,8 @@ constexpr int kDxBytes = kChunk * kTok * 4;                 // 256
 constexpr int kRedBytes = 2 * kOut * 4;                     // 2048: head and tail partial of the warp
 constexpr int kWarpBytes = kXbBytes + kDxBytes + kRedBytes; // 3328
 struct Params {
-    const uint2* sign_planes;
+    const uint4* planes;            // {sign0, sign1, salient0, salient1} per row (layers with zero weights) ...
+    const uint2* sign_planes;       // ... or the compact sign words only (kCompact)
     const float2* affine;
     const uint4* xb;
     const int* dx;
@@ -136,6 +137,7 @@ struct Params {
 };
 }  // namespace bsk
 
+template <bool kCompact>
 __global__ void __launch_bounds__(bsk::kThreads, 4) bireal_sk_kernel(const bsk::Params p) {
     using namespace bsk;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -161,11 +163,17 @@ __global__ void __launch_bounds__(bsk::kThreads, 4) bireal_sk_kernel(const bsk::
     uint32_t rg = 0, kb = 0;
     if (w_lo < w_hi) { rg = w_lo / TC; kb = w_lo - rg * TC; }
     const uint32_t rg_first = rg;
-    auto sign_ptr = [&](uint32_t r, uint32_t k) {            // tile-major compact planes: [tile row][k-block][128 rows]
-        return p.sign_planes + ((size_t)(r / kRgPerTile) * TC + k) * kTileRows + (r % kRgPerTile) * kRgRows + lane;
+    auto load_sg = [&](uint32_t r, uint32_t k) {             // tile-major planes: [tile row][k-block][128 rows]
+        const size_t i = ((size_t)(r / kRgPerTile) * TC + k) * kTileRows + (r % kRgPerTile) * kRgRows + lane;
+        if constexpr (kCompact) {
+            const uint2 v = __ldg(p.sign_planes + i);
+            return make_uint4(v.x, v.y, 0u, 0u);
+        } else {
+            return __ldg(p.planes + i);
+        }
     };
-    uint2 sg = make_uint2(0, 0);
-    if (w_lo < w_hi) sg = __ldg(sign_ptr(rg, kb));
+    uint4 sg = make_uint4(0, 0, 0, 0);
+    if (w_lo < w_hi) sg = load_sg(rg, kb);
     const bool grouped = p.groups > 1;
     uint32_t cur_g = grouped ? kb / p.tiles_per_group : 0u;
     float2 af = make_float2(0.f, 0.f);
@@ -186,13 +194,13 @@ __global__ void __launch_bounds__(bsk::kThreads, 4) bireal_sk_kernel(const bsk::
         if (ts) { const uint32_t f = owner(rg_b * TC); s_meta[6] = blockIdx.x - f; s_meta[7] = owner(rg_b * TC + TC - 1u) - f + 1u; }
     }
 
-    int d1[kTok], S[kTok];
+    int d1[kTok], d0[kTok];                                   // sum of sign(x) over the row's hi / lo positions
     float acc[kTok];
 #pragma unroll
-    for (int m = 0; m < kTok; ++m) { d1[m] = S[m] = 0; acc[m] = 0.f; }
+    for (int m = 0; m < kTok; ++m) { d1[m] = d0[m] = 0; acc[m] = 0.f; }
     auto fold = [&]() {                                       // counts -> values with the current {lo,hi}
 #pragma unroll
-        for (int m = 0; m < kTok; ++m) { acc[m] += af.y * (float)d1[m] + af.x * (float)(S[m] - d1[m]); d1[m] = S[m] = 0; }
+        for (int m = 0; m < kTok; ++m) { acc[m] += af.y * (float)d1[m] + af.x * (float)d0[m]; d1[m] = d0[m] = 0; }
     };
 
     // the activation bits come from the binarize kernel just before this one in the stream
@@ -232,15 +240,20 @@ __global__ void __launch_bounds__(bsk::kThreads, 4) bireal_sk_kernel(const bsk::
                 af = __ldg(p.affine + (size_t)(rg * kRgRows + lane) * p.groups + g);
             }
         }
-        const uint2 b = sg;
+        const uint4 b = sg;
         ++kb;
         const bool rg_end = kb == TC;
-        if (more) sg = __ldg(sign_ptr(rg_end ? rg + 1u : rg, rg_end ? 0u : kb));     // in-place prefetch of the next block
+        if (more) sg = load_sg(rg_end ? rg + 1u : rg, rg_end ? 0u : kb);             // in-place prefetch of the next block
+        bool any_sal = false;                                 // zero weights (sign(0) = 0) in this block of rows?
+        if constexpr (!kCompact) any_sal = __any_sync(0xffffffffu, (b.z | b.w) != 0u);
+        const uint32_t nb0 = ~(b.x | b.z), nb1 = ~(b.y | b.w);
 #pragma unroll
         for (int m = 0; m < kTok; ++m) {
             const uint4 xv = xs[ci * kTok + m];               // same address in every lane: a broadcast
-            d1[m] += __popc(b.x & xv.x) + __popc(b.y & xv.y) - __popc(b.x & xv.z) - __popc(b.y & xv.w);
-            S[m] += dxs[ci * kTok + m];
+            const int t1 = __popc(b.x & xv.x) + __popc(b.y & xv.y) - __popc(b.x & xv.z) - __popc(b.y & xv.w);
+            d1[m] += t1;
+            if (any_sal) d0[m] += __popc(nb0 & xv.x) + __popc(nb1 & xv.y) - __popc(nb0 & xv.z) - __popc(nb1 & xv.w);
+            else d0[m] += dxs[ci * kTok + m] - t1;            // no zero weights here: the lo set is the complement
         }
         ++ci;
         if (rg_end || !more) {
@@ -352,7 +365,7 @@ size_t bireal_workspace_bytes(const Layer& L, int64_t M) {
 // zero-initialised workspace the stream-K kernel needs for its cross-CTA reduction (same contract as the decode
 // kernel's: left zero by every call, one stream at a time); 0 when the layer does not qualify for that kernel
 size_t bireal_fixup_workspace_bytes(const Layer& L, int64_t M) {
-    if (!L.sign_planes || !bireal_sk_enabled() || M <= 0 || M > 64) return 0;   // larger M: the passes would re-read the planes
+    if (!bireal_sk_enabled() || M <= 0 || M > 64) return 0;   // larger M: the passes would re-read the planes
     return bireal_fixup_bytes(L, M);
 }
 int launch_bireal(const Layer& L, const void* x, int64_t ldx, int x_dtype, float* y, int64_t ldy, int64_t M, void* workspace,
@@ -370,14 +383,14 @@ int launch_bireal(const Layer& L, const void* x, int64_t ldx, int x_dtype, float
     int rc = check_cuda(cudaGetLastError(), "bireal binarize launch");
     if (rc) return rc;
     if (fixup_ws && fixup_bytes >= bireal_fixup_workspace_bytes(L, M) && bireal_fixup_workspace_bytes(L, M) > 0) {
-        // pure sign layer + a zeroed reduction workspace: stream-K kernel, balanced over all SMs
+        // a zeroed reduction workspace was given: stream-K kernel, balanced over all SMs
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
         uint32_t pl[8];
         decode_plan(L.N, L.K, M, sms, 4, pl);
         bsk::Params p;
-        p.sign_planes = L.sign_planes; p.affine = L.affine; p.xb = xb; p.dx = dx; p.y = y; p.ldy = ldy;
+        p.planes = L.planes; p.sign_planes = L.sign_planes; p.affine = L.affine; p.xb = xb; p.dx = dx; p.y = y; p.ldy = ldy;
         p.ws = reinterpret_cast<unsigned long long*>(fixup_ws);
         p.M = (int)M; p.N = (int)L.N;
         p.tiles_c = (uint32_t)L.tiles_c; p.groups = (uint32_t)L.groups; p.tiles_per_group = (uint32_t)L.tiles_per_group;
@@ -393,7 +406,7 @@ int launch_bireal(const Layer& L, const void* x, int64_t ldx, int x_dtype, float
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t le = cudaLaunchKernelEx(&cfg, bireal_sk_kernel, p);
+        cudaError_t le = L.sign_planes ? cudaLaunchKernelEx(&cfg, bireal_sk_kernel<true>, p) : cudaLaunchKernelEx(&cfg, bireal_sk_kernel<false>, p);
         count_launch(2);
         return check_cuda(le, "bireal stream-K launch");
     }

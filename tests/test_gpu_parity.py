@@ -737,3 +737,26 @@ def test_decode_kernel_activation_alignment_paths():
         ref = orc.linear(xv.float().cpu().numpy(), w)
         assert relmax(y, ref) <= 1e-3, off
         assert torch.equal(y, p.forward(xv.contiguous())), off       # same bits whatever the load path
+
+
+def test_bireal_stream_k_and_row_group_kernels_agree():
+    """pbl_bireal_forward_ws (stream-K XNOR kernel, zeroed reduction workspace) against pbl_bireal_forward (one CTA per
+    row group): same integer counts, fp32 folding in a different order; the stream-K result is repeatable bit for bit."""
+    lib = _lib.load()
+    for (N, K, M, zeros) in [(768, 768, 8, 0.0), (3072, 768, 5, 0.01), (130, 200, 19, 0.02), (4096, 4096, 8, 0.0)]:
+        rs = np.random.RandomState(N + K)
+        W = (rs.standard_normal((N, K)) * 0.02).astype(np.float32)
+        W[rs.rand(N, K) < zeros] = 0.0
+        m = pb.BiRealLinear(torch.from_numpy(W), None).to(DEV)
+        p = m.packed()
+        assert (p.sign_planes is not None) == (zeros == 0.0)
+        x = t(rounded(make_x(N + M, (M, K)), torch.float16), torch.float16)
+        y_new = p.bireal_forward(x)
+        assert int(lib.pbl_bireal_fixup_workspace(p.handle, M)) > 0
+        for _ in range(3):
+            assert torch.equal(y_new, p.bireal_forward(x))
+        y_old = torch.empty_like(y_new)
+        ws = torch.empty(p.bireal_workspace_bytes(M), dtype=torch.uint8, device=DEV)
+        rc = lib.pbl_bireal_forward(p.handle, x.data_ptr(), K, 0, y_old.data_ptr(), N, M, ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, _lib.last_error()
+        assert relmax(y_new, y_old.cpu().numpy()) <= 2e-6
