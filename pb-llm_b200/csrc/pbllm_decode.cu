@@ -460,13 +460,15 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
         } else {
             float sum[4] = {0.f, 0.f, 0.f, 0.f};
             for (uint32_t k = 0; k + 1u < expected; ++k) {
+                unsigned long long u[4];
+                do {                                         // four independent loads in flight per poll
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(u[j]) : "l"(part + (size_t)k * kOut + j) : "memory");
+                } while (((u[0] & u[1] & u[2] & u[3]) >> 32) == 0ull);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    unsigned long long u;
-                    do {
-                        asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(u) : "l"(part + (size_t)k * kOut + j) : "memory");
-                    } while ((u >> 32) == 0ull);
-                    sum[j] += __uint_as_float((uint32_t)u);
+                    sum[j] += __uint_as_float((uint32_t)u[j]);
                     asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(part + (size_t)k * kOut + j), "l"(0ull) : "memory");
                 }
             }
