@@ -11,11 +11,11 @@ python -c "import torch; torch.zeros(1).cuda()" > /dev/null 2>&1
 CS="compute-sanitizer --launch-timeout 300 --error-exitcode 9"
 if [ "${1:-all}" = "decode" ]; then
   timeout ${2:-200} $CS --tool racecheck python -m pytest tests/test_gpu_parity.py -m gpu -q \
-    -k "(decode_kernel_matches and (100-70 or 96-160 or 264-1030) and dtype0) or (decode_index_reproduces and 100-70 and dtype0)" \
+    -k "(decode_kernel_matches and (100-70 or 96-160 or 264-1030) and dtype0) or (decode_index_reproduces and 100-70 and dtype0) or (bireal_matches and (100-70 or 300-520) and xdtype0) or bireal_stream_k" \
     > gpurun_out/racecheck_decode.log 2>&1
   echo "racecheck rc=$?"; grep -E "RACECHECK SUMMARY|passed|failed|hazard" gpurun_out/racecheck_decode.log | tail -5
   timeout ${2:-200} $CS --tool memcheck python -m pytest tests/test_gpu_parity.py -m gpu -q \
-    -k "(decode_kernel_matches and (100-70 or 300-520 or 256-512 or 2048-128) and dtype0) or (decode_index_reproduces and dtype0) or decode_kernel_activation" \
+    -k "(decode_kernel_matches and (100-70 or 300-520 or 256-512 or 2048-128) and dtype0) or (decode_index_reproduces and dtype0) or decode_kernel_activation or (bireal_matches and (100-70 or 300-520 or 768-768)) or bireal_stream_k" \
     > gpurun_out/memcheck_decode.log 2>&1
   echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/memcheck_decode.log | tail -3
   exit 0
