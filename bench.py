@@ -165,7 +165,7 @@ def run_reference(args):
             "config": {"workload": workload_name(args), "parallelism": "host cores only"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_name(args):
@@ -174,7 +174,27 @@ def workload_name(args):
 
 
 # ---- our arm --------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout: point fd 1 at stderr while the run is going (NCCL prints its version
+    banner to stdout when NCCL_DEBUG is set, C libraries may print too) and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -495,7 +515,7 @@ def main():
                            "salient_fraction": nnz / nk * (world if rowshard else 1), "model_build_s": build_s},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks_summary(samples), "roofline": roofline,
                 "cpu_baseline": cb, "decode": decode, "xnor_popcount": xnor, "parity": parity}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
