@@ -25,8 +25,8 @@ _decode_ws_retired = []    # outgrown workspaces stay alive: captured CUDA graph
 
 
 def _decode_workspace(dev, stream_ptr: int, nbytes: int) -> torch.Tensor:
-    """Persistent per-(device, stream) workspace for pbl_linear_forward_ws: zeroed once here, the kernel leaves its
-    arrival counters at zero, so every layer on that stream shares it."""
+    """Persistent per-(device, stream) workspace for pbl_linear_forward_ws / pbl_bireal_forward_ws: zeroed once here,
+    every kernel that uses it leaves it zero again, so all layers on that stream share it."""
     key = (dev.index, stream_ptr)
     ws = _decode_ws.get(key)
     if ws is None or ws.numel() < nbytes:
