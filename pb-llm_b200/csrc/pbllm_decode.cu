@@ -33,8 +33,8 @@ constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kTok = 8;                       // tokens per pass (mma N)
 constexpr int kTileBytes = kRgRows * kTileCols * 2;   // 4096: the warp's 32x64 16-bit weight tile (128B rows, swizzled)
-constexpr int kHeadBytes = kRgRows * kTok * 4;        // 1024: the warp's head-segment partial (fp32 [8 tokens][32 rows])
-constexpr int kWarpBytes = kTileBytes + kHeadBytes;   // 5120
+constexpr int kHeadBytes = kRgRows * kTok * 4;        // 1024 per token group: the warp's head-segment partial (fp32 [tokens][32 rows])
+constexpr int kWarpBytes = kTileBytes + kHeadBytes;   // 5120 (one token group per pass); two groups: + kHeadBytes
 constexpr int kOut = kRgRows * kTok;          // 256 outputs per (row group, token pass) == kThreads
 static_assert(kOut == kThreads, "one thread per output in the cross-warp reduction");
 
@@ -123,9 +123,13 @@ __device__ __forceinline__ unsigned long long dk_now() {
     return t;
 }
 
-template <typename T, int kOcc, bool kTrace = false>
+// kNT = token groups of 8 per pass: 1 (M <= 8), or 2 (9..16 tokens against ONE expansion of each tile; the second group
+// lives in its own variables, so the one-group instance compiles to exactly the code it had before)
+template <typename T, int kOcc, bool kTrace = false, int kNT = 1>
 __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk::Params p) {
     using namespace dk;
+    constexpr int kWarpBytes = dk::kWarpBytes + (kNT - 1) * kHeadBytes;
+    constexpr int kTokP = kTok * kNT, kOutP = kOut * kNT;
     unsigned long long tr[8];
     if (kTrace) { tr[0] = dk_now(); }
     extern __shared__ __align__(128) uint8_t smem[];
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     const uint32_t gw0 = blockIdx.x * kWarps;
     const uint32_t c_lo = wstart(gw0), c_hi = wstart(gw0 + kWarps);
     const uint32_t w_lo = wstart(gw0 + wid), w_hi = wstart(gw0 + wid + 1u);
-    const int m0 = blockIdx.y * kTok;
+    const int m0 = blockIdx.y * kTokP;
 
     // Programmatic dependent launch: the next kernel in the stream may start its own weight prefetch now; everything
     // below up to griddepcontrol.wait touches only immutable packed weights.
@@ -217,34 +221,39 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     uint32_t xoff_row = (uint32_t)(((int64_t)(m0 + (x_tok_ok ? (int)xtok : 0)) * p.ldx + 16 * xseg) * 2);
     asm volatile("" : "+r"(xoff_row));
     uint32_t xoff = xoff_row + kb * (kTileCols * 2u);          // loop-carried: advances one k-block per iteration
+    const bool x_tok_ok2 = kNT == 2 && (m0 + kTok + (int)xtok) < p.M;                      // second token group
+    uint32_t xoff_row2 = (uint32_t)(((int64_t)(x_tok_ok2 ? m0 + kTok + (int)xtok : m0) * p.ldx + 16 * xseg) * 2);
+    if constexpr (kNT == 2) asm volatile("" : "+r"(xoff_row2));
+    uint32_t xoff2 = xoff_row2 + kb * (kTileCols * 2u);
     const uint8_t* xbytes = reinterpret_cast<const uint8_t*>(p.x);
     // fast path (x_fast: 16 B aligned rows, K a multiple of 64): two unconditional 16 B loads -- rows past M read token
     // m0's row, whose products land in output columns that are never stored.  Anything else: bounds-checked elements.
-    auto load_x = [&](uint32_t kblk, uint4& xa, uint4& xb) {
+    auto load_x_at = [&](uint32_t kblk, uint32_t off, bool tok_ok, uint4& xa, uint4& xb) {
         if (x_fast256) {                               // sm_100 256-bit load: half the L1 wavefronts of two 128-bit loads
             asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                          : "=r"(xa.x), "=r"(xa.y), "=r"(xa.z), "=r"(xa.w), "=r"(xb.x), "=r"(xb.y), "=r"(xb.z), "=r"(xb.w)
-                         : "l"(xbytes + xoff));
+                         : "l"(xbytes + off));
         } else if (x_fast) {
-            const uint4* p4 = reinterpret_cast<const uint4*>(xbytes + xoff);
+            const uint4* p4 = reinterpret_cast<const uint4*>(xbytes + off);
             xa = __ldg(p4);
             xb = __ldg(p4 + 1);
         } else {
-            const uint16_t* qx = reinterpret_cast<const uint16_t*>(xbytes + xoff);
+            const uint16_t* qx = reinterpret_cast<const uint16_t*>(xbytes + off);
             const int col = (int)(kblk * kTileCols + 16 * xseg);
             uint32_t w[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int cc = col + 2 * i;
                 uint32_t v = 0;
-                if (x_tok_ok && cc < p.K) v = (uint32_t)qx[2 * i];
-                if (x_tok_ok && cc + 1 < p.K) v |= (uint32_t)qx[2 * i + 1] << 16;
+                if (tok_ok && cc < p.K) v = (uint32_t)qx[2 * i];
+                if (tok_ok && cc + 1 < p.K) v |= (uint32_t)qx[2 * i + 1] << 16;
                 w[i] = v;
             }
             xa = make_uint4(w[0], w[1], w[2], w[3]);
             xb = make_uint4(w[4], w[5], w[6], w[7]);
         }
     };
+    auto load_x = [&](uint32_t kblk, uint4& xa, uint4& xb) { load_x_at(kblk, xoff, x_tok_ok, xa, xb); };
 
     // shared-memory addresses of this lane
     const uint32_t r7 = lane & 7u;
@@ -261,9 +270,9 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     uint32_t brow_r = brow;
     asm volatile("" : "+r"(brow_r));
 
-    float acc[2][4];
+    float acc[2][4], acc2[2][4];                  // acc2: second token group (kNT == 2)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[0][i] = acc[1][i] = 0.f;
+    for (int i = 0; i < 4; ++i) acc[0][i] = acc[1][i] = acc2[0][i] = acc2[1][i] = 0.f;
 
     // fp32 [token][row] layout of one row group's outputs: index m*32 + r
     auto store_frag = [&](float* dst) {
@@ -274,6 +283,12 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
             dst[(2u * t4 + 1u) * kRgRows + r] = acc[h][1];
             dst[(2u * t4) * kRgRows + r + 8u] = acc[h][2];
             dst[(2u * t4 + 1u) * kRgRows + r + 8u] = acc[h][3];
+            if constexpr (kNT == 2) {
+                dst[kOut + (2u * t4) * kRgRows + r] = acc2[h][0];
+                dst[kOut + (2u * t4 + 1u) * kRgRows + r] = acc2[h][1];
+                dst[kOut + (2u * t4) * kRgRows + r + 8u] = acc2[h][2];
+                dst[kOut + (2u * t4 + 1u) * kRgRows + r + 8u] = acc2[h][3];
+            }
         }
     };
 
@@ -282,7 +297,9 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (kTrace) tr[2] = dk_now();
     uint4 xa = make_uint4(0, 0, 0, 0), xb = make_uint4(0, 0, 0, 0);
+    uint4 xa2 = make_uint4(0, 0, 0, 0), xb2 = make_uint4(0, 0, 0, 0);
     if (w_lo < w_hi) load_x(kb, xa, xb);
+    if constexpr (kNT == 2) { if (w_lo < w_hi) load_x_at(kb, xoff2, x_tok_ok2, xa2, xb2); }
 
     // Every stream is prefetched IN PLACE: a register set is reloaded right after its last use (sign words, activations:
     // one block of cover; salient entries, the stream that comes from DRAM with a dependent address: two sets, two blocks).
@@ -323,6 +340,7 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
         // tensor cores: A fragments by ldmatrix from the tile, B fragments straight from the activation registers
         {
             const uint32_t xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            const uint32_t xw2[8] = {xa2.x, xa2.y, xa2.z, xa2.w, xb2.x, xb2.y, xb2.z, xb2.w};
 #pragma unroll
             for (int qi = 0; qi < 4; ++qi) {
 #pragma unroll
@@ -330,6 +348,7 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
                     uint32_t a0, a1, a2, a3;
                     dk_ldsm4(lm_q[qi] + (uint32_t)h * 2048u, a0, a1, a2, a3);
                     dk_mma<T>(acc[h], a0, a1, a2, a3, xw[2 * qi], xw[2 * qi + 1]);
+                    if constexpr (kNT == 2) dk_mma<T>(acc2[h], a0, a1, a2, a3, xw2[2 * qi], xw2[2 * qi + 1]);
                 }
             }
         }
@@ -337,6 +356,10 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
         const bool rg_end = kb == TC;
         xoff = rg_end ? xoff_row : xoff + kTileCols * 2u;
         load_x(rg_end ? 0u : kb, xa, xb);               // unconditional: the address after the last block is still inside x
+        if constexpr (kNT == 2) {
+            xoff2 = rg_end ? xoff_row2 : xoff2 + kTileCols * 2u;
+            load_x_at(rg_end ? 0u : kb, xoff2, x_tok_ok2, xa2, xb2);
+        }
 
         // ---- end of this warp's part of the row group? -----------------------------------------------------
         if (rg_end || !more) {
@@ -349,7 +372,7 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
                 if (orow < p.N) {
                     const float bv = p.bias ? p.bias[orow] : 0.f;
 #pragma unroll
-                    for (int m = 0; m < kTok; ++m)
+                    for (int m = 0; m < kTokP; ++m)
                         if (m0 + m < p.M)
                             reinterpret_cast<T*>(p.y)[(int64_t)(m0 + m) * p.ldy + orow] = from_f32<T>(bv + tail_red[m * kRgRows + lane]);
                 }
@@ -362,7 +385,7 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
                 if (lane == 0) s_trg[wid] = rg;
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[0][i] = acc[1][i] = 0.f;
+            for (int i = 0; i < 4; ++i) acc[0][i] = acc[1][i] = acc2[0][i] = acc2[1][i] = 0.f;
             if (rg_end) {
                 kb = 0;
                 ++rg;
@@ -401,8 +424,14 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     if (tid >= 64u) { if (kTrace) tr[5] = tr[4]; trace_out(); return; }
     const uint32_t rg_a = s_meta[0], rg_b = s_meta[1];
     const uint32_t om = tid >> 3, or4 = (tid & 7u) * 4u;
-    T* yout = reinterpret_cast<T*>(p.y) + (int64_t)(m0 + om) * p.ldy;
-    const bool tok_ok = (m0 + (int)om) < p.M;
+    uint32_t hrg[kWarps], trg[kWarps];
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) { hrg[w] = s_hrg[w]; trg[w] = s_trg[w]; }
+    const bool hs = s_meta[2] != 0u, ts = s_meta[5] != 0u;
+#pragma unroll
+    for (int u = 0; u < kNT; ++u) {                          // one round per token group: float4 number 64u + t of the buffers
+    T* yout = reinterpret_cast<T*>(p.y) + (int64_t)(m0 + kTok * u + om) * p.ldy;
+    const bool tok_ok = (m0 + kTok * u + (int)om) < p.M;
     auto emit = [&](uint32_t r, const float4 v) {            // + bias, round, store the four outputs of row group r
         const int orow = (int)(r * kRgRows + or4);
         const float vv[4] = {v.x, v.y, v.z, v.w};
@@ -412,9 +441,6 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
                 if (orow + j < p.N) yout[orow + j] = from_f32<T>((p.bias ? p.bias[orow + j] : 0.f) + vv[j]);
         }
     };
-    uint32_t hrg[kWarps], trg[kWarps];
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) { hrg[w] = s_hrg[w]; trg[w] = s_trg[w]; }
     float4 v_split[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};   // head / tail row group (when shared)
     for (uint32_t r = rg_a; r <= rg_b; ++r) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -422,11 +448,11 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {                   // fixed order: warp 0's partial first
             if (hrg[w] == r) {
-                const float4 a4 = reinterpret_cast<const float4*>(smem + w * kWarpBytes + kTileBytes)[tid];
+                const float4 a4 = reinterpret_cast<const float4*>(smem + w * kWarpBytes + kTileBytes)[64 * u + tid];
                 v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w; any = true;
             }
             if (trg[w] == r) {
-                const float4 a4 = reinterpret_cast<const float4*>(smem + w * kWarpBytes)[tid];
+                const float4 a4 = reinterpret_cast<const float4*>(smem + w * kWarpBytes)[64 * u + tid];
                 v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w; any = true;
             }
         }
@@ -436,9 +462,8 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
         else if (r == rg_a) v_split[0] = v;
         else v_split[1] = v;
     }
-    const bool hs = s_meta[2] != 0u, ts = s_meta[5] != 0u;
     if (kTrace) tr[5] = dk_now();
-    if (!hs && !ts) { trace_out(); return; }
+    if (!hs && !ts) continue;
     // Row groups shared with other CTAs.  Every contributor but the last parks its partial in its own slot as 64-bit
     // stores {value, valid tag}: data and flag travel together, so there is no fence, no counter and no barrier.  The
     // last contributor (highest CTA index, so everything it waits for was scheduled before it) polls the slots, sums them
@@ -448,14 +473,14 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     for (int f = 1; f >= 0; --f) {                           // the tail group first: this CTA is never its last contributor
         if (!(f == 0 ? hs : ts)) continue;
         const uint32_t r = f == 0 ? rg_a : rg_b, slot = s_meta[f == 0 ? 3 : 6], expected = s_meta[f == 0 ? 4 : 7];
-        unsigned long long* part = ws + (((size_t)blockIdx.y * p.rgs + r) * p.slots) * kOut + tid * 4u;
+        unsigned long long* part = ws + (((size_t)blockIdx.y * p.rgs + r) * p.slots) * kOutP + kOut * u + tid * 4u;
         const float4 v = v_split[f];
         const float vv[4] = {v.x, v.y, v.z, v.w};
         if (slot + 1u < expected) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const unsigned long long u = (1ull << 32) | (unsigned long long)__float_as_uint(vv[j]);
-                asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(part + (size_t)slot * kOut + j), "l"(u) : "memory");
+                asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(part + (size_t)slot * kOutP + j), "l"(u) : "memory");
             }
         } else {
             float sum[4] = {0.f, 0.f, 0.f, 0.f};
@@ -464,16 +489,17 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
                 do {                                         // four independent loads in flight per poll
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(u[j]) : "l"(part + (size_t)k * kOut + j) : "memory");
+                        asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(u[j]) : "l"(part + (size_t)k * kOutP + j) : "memory");
                 } while (((u[0] & u[1] & u[2] & u[3]) >> 32) == 0ull);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     sum[j] += __uint_as_float((uint32_t)u[j]);
-                    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(part + (size_t)k * kOut + j), "l"(0ull) : "memory");
+                    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(part + (size_t)k * kOutP + j), "l"(0ull) : "memory");
                 }
             }
             emit(r, make_float4(sum[0] + vv[0], sum[1] + vv[1], sum[2] + vv[2], sum[3] + vv[3]));
         }
+    }
     }
     trace_out();
 }
@@ -622,12 +648,13 @@ void decode_set_trace(void* buf, size_t bytes) {
     g_trace_next = 0;
 }
 
-struct DecodeGeom { uint32_t nblocks, rgs, grid, slots, passes, q, rem; size_t ws_bytes; };
+struct DecodeGeom { uint32_t nblocks, rgs, grid, slots, passes, q, rem, nt; size_t ws_bytes; };
 
 static DecodeGeom decode_geom_raw(int64_t tiles_r, int64_t tiles_c, int64_t M, uint32_t want);
 
 static DecodeGeom decode_geom(const Layer& L, int64_t M) {
-    return decode_geom_raw(L.tiles_r, L.tiles_c, M, (uint32_t)(dk_num_sms() * dk_ctas_per_sm()));
+    const int ctas = M > dk::kTok ? (dk_ctas_per_sm() < 2 ? dk_ctas_per_sm() : 2) : dk_ctas_per_sm();   // 16-token passes: 2 CTAs per SM
+    return decode_geom_raw(L.tiles_r, L.tiles_c, M, (uint32_t)(dk_num_sms() * ctas));
 }
 
 // host-only: the launch plan of the decode kernel for an N x K layer on a device with `sms` SMs (pbl_decode_plan)
@@ -649,8 +676,9 @@ static DecodeGeom decode_geom_raw(int64_t tiles_r, int64_t tiles_c, int64_t M, u
     g.rem = g.nblocks % (g.grid * dk::kWarps);
     // a CTA's run is at least 8*q blocks long, so a row group (tiles_c blocks) meets at most this many CTAs
     g.slots = g.q ? ((uint32_t)L.tiles_c + 8u * g.q - 1u) / (8u * g.q) + 1u : 2u;
-    g.passes = (uint32_t)((M + dk::kTok - 1) / dk::kTok);
-    g.ws_bytes = (size_t)g.passes * g.rgs * g.slots * dk::kOut * 8u;
+    g.nt = M > dk::kTok ? 2u : 1u;                                                     // token groups of 8 per pass
+    g.passes = (uint32_t)((M + dk::kTok * g.nt - 1) / (dk::kTok * g.nt));
+    g.ws_bytes = (size_t)g.passes * g.rgs * g.slots * dk::kOut * g.nt * 8u;
     return g;
 }
 
@@ -667,16 +695,16 @@ size_t decode_workspace_bytes(const Layer& L, int64_t M) {
     return decode_geom(L, M).ws_bytes;
 }
 
-template <typename T, int kOcc>
+template <typename T, int kOcc, int kNT>
 static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws, cudaStream_t s) {
     const DecodeGeom g = decode_geom(L, M);
-    const int smem = dk::kWarps * dk::kWarpBytes;
+    const int smem = dk::kWarps * (dk::kWarpBytes + (kNT - 1) * dk::kHeadBytes);
     static int attr_smem_dev[64] = {};   // function attributes are per device
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
     if (cur_dev < 0 || cur_dev >= 64) cur_dev = 0;
     if (attr_smem_dev[cur_dev] < smem) {
-        int rc = check_cuda(cudaFuncSetAttribute(decode_mma_kernel<T, kOcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+        int rc = check_cuda(cudaFuncSetAttribute(decode_mma_kernel<T, kOcc, false, kNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                             "cudaFuncSetAttribute(decode smem)");
         if (rc) return rc;
         attr_smem_dev[cur_dev] = smem;
@@ -702,14 +730,14 @@ static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, 
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     cudaError_t le;
-    if (g_trace && g_trace_next < g_trace_launches && kOcc == 3) {
+    if (g_trace && g_trace_next < g_trace_launches && kOcc == 3 && kNT == 1) {
         p.trace = g_trace + (g_trace_next++) * kTraceStride;
         static bool tattr = false;
         if (!tattr) { cudaFuncSetAttribute(decode_mma_kernel<T, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); tattr = true; }
         le = cudaLaunchKernelEx(&cfg, decode_mma_kernel<T, 3, true>, p);
     } else {
         p.trace = nullptr;
-        le = cudaLaunchKernelEx(&cfg, decode_mma_kernel<T, kOcc>, p);
+        le = cudaLaunchKernelEx(&cfg, decode_mma_kernel<T, kOcc, false, kNT>, p);
     }
     count_launch();
     return check_cuda(le, "decode launch");
@@ -732,12 +760,15 @@ int launch_decode(const Layer& L, const void* x, int64_t ldx, void* y, int64_t l
         ws = own;
     }
     int rc;
-    if (dk_occupancy() == 4)
-        rc = (L.dtype == PBL_F16) ? launch_decode_t<__half, 4>(L, x, ldx, y, ldy, M, ws, s)
-                                  : launch_decode_t<__nv_bfloat16, 4>(L, x, ldx, y, ldy, M, ws, s);
+    if (g.nt == 2)                                       // 9..16 tokens in one pass: 128 registers, 2 CTAs per SM
+        rc = (L.dtype == PBL_F16) ? launch_decode_t<__half, 2, 2>(L, x, ldx, y, ldy, M, ws, s)
+                                  : launch_decode_t<__nv_bfloat16, 2, 2>(L, x, ldx, y, ldy, M, ws, s);
+    else if (dk_occupancy() == 4)
+        rc = (L.dtype == PBL_F16) ? launch_decode_t<__half, 4, 1>(L, x, ldx, y, ldy, M, ws, s)
+                                  : launch_decode_t<__nv_bfloat16, 4, 1>(L, x, ldx, y, ldy, M, ws, s);
     else
-        rc = (L.dtype == PBL_F16) ? launch_decode_t<__half, 3>(L, x, ldx, y, ldy, M, ws, s)
-                                  : launch_decode_t<__nv_bfloat16, 3>(L, x, ldx, y, ldy, M, ws, s);
+        rc = (L.dtype == PBL_F16) ? launch_decode_t<__half, 3, 1>(L, x, ldx, y, ldy, M, ws, s)
+                                  : launch_decode_t<__nv_bfloat16, 3, 1>(L, x, ldx, y, ldy, M, ws, s);
     if (own) {
         const int rf = check_cuda(cudaFreeAsync(own, s), "cudaFreeAsync(decode workspace)");
         if (!rc) rc = rf;

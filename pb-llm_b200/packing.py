@@ -156,7 +156,8 @@ class PackedLinear:
             _lib.check(lib.pbl_layer_attach_decode_index(self.handle, C.c_void_p(dsign.data_ptr()), C.c_void_p(eptr.data_ptr()),
                                                          C.c_void_p(ent.data_ptr())), "pbl_layer_attach_decode_index")
         self.dsign, self.eptr, self.ent = dsign, eptr, ent
-        self._dws_bytes = int(lib.pbl_decode_workspace_bytes(self.handle, DECODE_MAX_M))
+        # one-group passes (M <= 8) and two-group passes (9..16) use different grids: take the larger need
+        self._dws_bytes = max(int(lib.pbl_decode_workspace_bytes(self.handle, 8)), int(lib.pbl_decode_workspace_bytes(self.handle, DECODE_MAX_M)))
 
     def drop_decode_index(self):
         _lib.check(_lib.load().pbl_layer_attach_decode_index(self.handle, None, None, None), "pbl_layer_attach_decode_index")

@@ -104,8 +104,10 @@ def test_plan_partition_is_exact_and_slots_suffice(N, K, ctas):
 
 
 def test_plan_token_passes_and_errors():
-    assert plan(4096, 4096, 8, 148, 3)["passes"] == 1 and plan(4096, 4096, 9, 148, 3)["passes"] == 2
-    assert plan(4096, 4096, 16, 148, 3)["ws_kib"] == 2 * plan(4096, 4096, 8, 148, 3)["ws_kib"]
+    # up to 8 tokens: one group per pass; 9..16: two groups against one expansion of each tile, still one pass
+    assert plan(4096, 4096, 8, 148, 3)["passes"] == 1 and plan(4096, 4096, 9, 148, 3)["passes"] == 1
+    assert plan(4096, 4096, 16, 148, 3)["passes"] == 1 and plan(4096, 4096, 17, 148, 3)["passes"] == 2
+    assert plan(4096, 4096, 16, 148, 2)["ws_kib"] == 2 * plan(4096, 4096, 8, 148, 2)["ws_kib"]   # same grid, twice the outputs
     out = (C.c_uint32 * 8)()
     assert _lib.load().pbl_decode_plan(0, 64, 1, 148, 3, out) == -3
     assert _lib.load().pbl_decode_plan(64, 64, 1, 148, 3, None) == -1
