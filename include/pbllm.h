@@ -166,7 +166,8 @@ PBL_API int pbl_linear_forward_ws(const pbl_layer* layer, const void* x, int64_t
                                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* Host-only: the decode kernel's launch plan for an N x K layer, M tokens, on a device with `sms` SMs and
- * `ctas_per_sm` CTAs of 8 warps per SM.  out8 = {blocks, row groups, grid.x, token passes, q, rem, slots, workspace KiB}:
+ * `ctas_per_sm` CTAs of 8 warps per SM (a pass handles 8 tokens, or 16 when M > 8).  out8 = {blocks, row groups, grid.x,
+ * token passes, q, rem, slots, workspace KiB}:
  * warp g of the grid owns blocks [g*q + min(g, rem), (g+1)*q + min(g+1, rem)) of the row-group-major block order, and a
  * row group's partials need at most `slots` workspace slots (tests/test_decode_plan.py checks both on the CPU). */
 PBL_API int pbl_decode_plan(int64_t N, int64_t K, int64_t M, int sms, int ctas_per_sm, uint32_t* out8);
