@@ -419,8 +419,9 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
             for (int i = 0; i < 8; ++i) o[i] = tr[i];
         }
     };
-    // Two warps finish the CTA: thread t < 64 owns four consecutive outputs -- token t>>3, rows 4*(t&7)..+3 of the row group,
-    // i.e. float4 number t of every [token][row] partial buffer -- so each partial costs one LDS.128 per thread.
+    // Two warps finish the CTA: thread t < 64 owns four consecutive outputs per token group -- token 8u + (t>>3), rows
+    // 4*(t&7)..+3 of the row group, i.e. float4 number 64u + t of every [token][row] partial buffer -- so each partial costs
+    // one LDS.128 per thread and group.
     if (tid >= 64u) { if (kTrace) tr[5] = tr[4]; trace_out(); return; }
     const uint32_t rg_a = s_meta[0], rg_b = s_meta[1];
     const uint32_t om = tid >> 3, or4 = (tid & 7u) * 4u;
@@ -430,76 +431,76 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     const bool hs = s_meta[2] != 0u, ts = s_meta[5] != 0u;
 #pragma unroll
     for (int u = 0; u < kNT; ++u) {                          // one round per token group: float4 number 64u + t of the buffers
-    T* yout = reinterpret_cast<T*>(p.y) + (int64_t)(m0 + kTok * u + om) * p.ldy;
-    const bool tok_ok = (m0 + kTok * u + (int)om) < p.M;
-    auto emit = [&](uint32_t r, const float4 v) {            // + bias, round, store the four outputs of row group r
-        const int orow = (int)(r * kRgRows + or4);
-        const float vv[4] = {v.x, v.y, v.z, v.w};
-        if (tok_ok) {
+        T* yout = reinterpret_cast<T*>(p.y) + (int64_t)(m0 + kTok * u + om) * p.ldy;
+        const bool tok_ok = (m0 + kTok * u + (int)om) < p.M;
+        auto emit = [&](uint32_t r, const float4 v) {            // + bias, round, store the four outputs of row group r
+            const int orow = (int)(r * kRgRows + or4);
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+            if (tok_ok) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (orow + j < p.N) yout[orow + j] = from_f32<T>((p.bias ? p.bias[orow + j] : 0.f) + vv[j]);
-        }
-    };
-    float4 v_split[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};   // head / tail row group (when shared)
-    for (uint32_t r = rg_a; r <= rg_b; ++r) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        bool any = false;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {                   // fixed order: warp 0's partial first
-            if (hrg[w] == r) {
-                const float4 a4 = reinterpret_cast<const float4*>(smem + w * kWarpBytes + kTileBytes)[64 * u + tid];
-                v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w; any = true;
+                for (int j = 0; j < 4; ++j)
+                    if (orow + j < p.N) yout[orow + j] = from_f32<T>((p.bias ? p.bias[orow + j] : 0.f) + vv[j]);
             }
-            if (trg[w] == r) {
-                const float4 a4 = reinterpret_cast<const float4*>(smem + w * kWarpBytes)[64 * u + tid];
-                v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w; any = true;
-            }
-        }
-        if (!any) continue;                                  // stored by the single warp that owned it
-        const bool split = (r == rg_a && s_meta[2]) || (r == rg_b && s_meta[5]);
-        if (!split) emit(r, v);                              // the whole row group lives in this CTA
-        else if (r == rg_a) v_split[0] = v;
-        else v_split[1] = v;
-    }
-    if (kTrace) tr[5] = dk_now();
-    if (!hs && !ts) continue;
-    // Row groups shared with other CTAs.  Every contributor but the last parks its partial in its own slot as 64-bit
-    // stores {value, valid tag}: data and flag travel together, so there is no fence, no counter and no barrier.  The
-    // last contributor (highest CTA index, so everything it waits for was scheduled before it) polls the slots, sums them
-    // in CTA order (deterministic), clears them for the next kernel, and writes y.
-    unsigned long long* ws = reinterpret_cast<unsigned long long*>(p.ws_part);
+        };
+        float4 v_split[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};   // head / tail row group (when shared)
+        for (uint32_t r = rg_a; r <= rg_b; ++r) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool any = false;
 #pragma unroll
-    for (int f = 1; f >= 0; --f) {                           // the tail group first: this CTA is never its last contributor
-        if (!(f == 0 ? hs : ts)) continue;
-        const uint32_t r = f == 0 ? rg_a : rg_b, slot = s_meta[f == 0 ? 3 : 6], expected = s_meta[f == 0 ? 4 : 7];
-        unsigned long long* part = ws + (((size_t)blockIdx.y * p.rgs + r) * p.slots) * kOutP + kOut * u + tid * 4u;
-        const float4 v = v_split[f];
-        const float vv[4] = {v.x, v.y, v.z, v.w};
-        if (slot + 1u < expected) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const unsigned long long u = (1ull << 32) | (unsigned long long)__float_as_uint(vv[j]);
-                asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(part + (size_t)slot * kOutP + j), "l"(u) : "memory");
-            }
-        } else {
-            float sum[4] = {0.f, 0.f, 0.f, 0.f};
-            for (uint32_t k = 0; k + 1u < expected; ++k) {
-                unsigned long long u[4];
-                do {                                         // four independent loads in flight per poll
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(u[j]) : "l"(part + (size_t)k * kOutP + j) : "memory");
-                } while (((u[0] & u[1] & u[2] & u[3]) >> 32) == 0ull);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    sum[j] += __uint_as_float((uint32_t)u[j]);
-                    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(part + (size_t)k * kOutP + j), "l"(0ull) : "memory");
+            for (int w = 0; w < kWarps; ++w) {                   // fixed order: warp 0's partial first
+                if (hrg[w] == r) {
+                    const float4 a4 = reinterpret_cast<const float4*>(smem + w * kWarpBytes + kTileBytes)[64 * u + tid];
+                    v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w; any = true;
+                }
+                if (trg[w] == r) {
+                    const float4 a4 = reinterpret_cast<const float4*>(smem + w * kWarpBytes)[64 * u + tid];
+                    v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w; any = true;
                 }
             }
-            emit(r, make_float4(sum[0] + vv[0], sum[1] + vv[1], sum[2] + vv[2], sum[3] + vv[3]));
+            if (!any) continue;                                  // stored by the single warp that owned it
+            const bool split = (r == rg_a && s_meta[2]) || (r == rg_b && s_meta[5]);
+            if (!split) emit(r, v);                              // the whole row group lives in this CTA
+            else if (r == rg_a) v_split[0] = v;
+            else v_split[1] = v;
         }
-    }
+        if (kTrace) tr[5] = dk_now();
+        if (!hs && !ts) continue;
+        // Row groups shared with other CTAs.  Every contributor but the last parks its partial in its own slot as 64-bit
+        // stores {value, valid tag}: data and flag travel together, so there is no fence, no counter and no barrier.  The
+        // last contributor (highest CTA index, so everything it waits for was scheduled before it) polls the slots, sums them
+        // in CTA order (deterministic), clears them for the next kernel, and writes y.
+        unsigned long long* ws = reinterpret_cast<unsigned long long*>(p.ws_part);
+#pragma unroll
+        for (int f = 1; f >= 0; --f) {                           // the tail group first: this CTA is never its last contributor
+            if (!(f == 0 ? hs : ts)) continue;
+            const uint32_t r = f == 0 ? rg_a : rg_b, slot = s_meta[f == 0 ? 3 : 6], expected = s_meta[f == 0 ? 4 : 7];
+            unsigned long long* part = ws + (((size_t)blockIdx.y * p.rgs + r) * p.slots) * kOutP + kOut * u + tid * 4u;
+            const float4 v = v_split[f];
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+            if (slot + 1u < expected) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned long long w64 = (1ull << 32) | (unsigned long long)__float_as_uint(vv[j]);
+                    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(part + (size_t)slot * kOutP + j), "l"(w64) : "memory");
+                }
+            } else {
+                float sum[4] = {0.f, 0.f, 0.f, 0.f};
+                for (uint32_t k = 0; k + 1u < expected; ++k) {
+                    unsigned long long w64[4];
+                    do {                                         // four independent loads in flight per poll
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w64[j]) : "l"(part + (size_t)k * kOutP + j) : "memory");
+                    } while (((w64[0] & w64[1] & w64[2] & w64[3]) >> 32) == 0ull);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        sum[j] += __uint_as_float((uint32_t)w64[j]);
+                        asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(part + (size_t)k * kOutP + j), "l"(0ull) : "memory");
+                    }
+                }
+                emit(r, make_float4(sum[0] + vv[0], sum[1] + vv[1], sum[2] + vv[2], sum[3] + vv[3]));
+            }
+        }
     }
     trace_out();
 }
