@@ -83,8 +83,8 @@ def load():
         try:
             path = _build.build()
         except Exception as e:  # noqa: BLE001
-            if not os.path.exists(path):
-                raise RuntimeError(f"libpbllm.so is missing and could not be built: {e}") from e
+            # never load a binary that was built from other sources than the ones in the tree
+            raise RuntimeError(f"libpbllm.so is missing or stale (source hash mismatch) and could not be rebuilt: {e}") from e
     try:
         lib = C.CDLL(path)
     except OSError as e:

@@ -24,12 +24,31 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; libpbllm.so cannot be built")
 
 
+HASHFILE = LIB + ".srchash"
+
+
+def source_hash() -> str:
+    """sha256 over the kernel sources, the public header and the compiler flags: what the .so was built from.
+    (mtimes do not survive the snapshot copy to the GPU box; contents do.)"""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS + SOURCES).encode())
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(os.path.dirname(HERE), "include", "pbllm.h")]
+    for d in deps:
+        with open(d, "rb") as f:
+            h.update(os.path.basename(d).encode() + b"\0" + f.read())
+    return h.hexdigest()
+
+
+def built_hash() -> str:
+    try:
+        with open(HASHFILE) as f:
+            return f.read().strip()
+    except OSError:
+        return ""
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(os.path.dirname(HERE), "include", "pbllm.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return not os.path.exists(LIB) or built_hash() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -44,6 +63,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
+    with open(HASHFILE, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB
 
 

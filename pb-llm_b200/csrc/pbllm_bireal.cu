@@ -349,13 +349,17 @@ static int bireal_sk_enabled() {
     return v;
 }
 
+// bireal_sk_kernel handles bsk::kTok = 8 tokens per blockIdx.y whatever M is (the decode kernel's plan switches to
+// 16-token passes above 8 tokens, so its `passes` must not be used here)
+static uint32_t bireal_passes(int64_t M) { return (uint32_t)((M + bsk::kTok - 1) / bsk::kTok); }
+
 static size_t bireal_fixup_bytes(const Layer& L, int64_t M) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) { (void)cudaGetLastError(); sms = 148; }
     uint32_t pl[8];
-    decode_plan(L.N, L.K, M, sms, 4, pl);
-    return (size_t)pl[3] * pl[1] * pl[6] * bsk::kOut * 8u;
+    decode_plan(L.N, L.K, 1, sms, 4, pl);       // block partition only: this kernel's token passes are its own (8 tokens each)
+    return (size_t)bireal_passes(M) * pl[1] * pl[6] * bsk::kOut * 8u;
 }
 
 size_t bireal_workspace_bytes(const Layer& L, int64_t M) {
@@ -388,7 +392,7 @@ int launch_bireal(const Layer& L, const void* x, int64_t ldx, int x_dtype, float
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
         uint32_t pl[8];
-        decode_plan(L.N, L.K, M, sms, 4, pl);
+        decode_plan(L.N, L.K, 1, sms, 4, pl);
         bsk::Params p;
         p.planes = L.planes; p.sign_planes = L.sign_planes; p.affine = L.affine; p.xb = xb; p.dx = dx; p.y = y; p.ldy = ldy;
         p.ws = reinterpret_cast<unsigned long long*>(fixup_ws);
@@ -397,7 +401,7 @@ int launch_bireal(const Layer& L, const void* x, int64_t ldx, int x_dtype, float
         p.rgs = pl[1]; p.slots = pl[6]; p.q = pl[4]; p.rem = pl[5];
         const int smem = bsk::kWarps * bsk::kWarpBytes;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(pl[2], pl[3]);
+        cfg.gridDim = dim3(pl[2], bireal_passes(M));
         cfg.blockDim = dim3(bsk::kThreads);
         cfg.dynamicSmemBytes = (size_t)smem;
         cfg.stream = s;

@@ -276,6 +276,16 @@ class PackedLinear:
                        "pbl_unpack")
         return w
 
+    def low_mask_dense(self) -> torch.Tensor:
+        """bool [N,K], True = binarized position (the complement of the packed salient bitmap). One-time utility
+        (re-packing in another dtype for autocast); decoded from the planes with torch bit ops."""
+        sz = self.sizes
+        pl = self.planes.view(sz.tiles_r, sz.tiles_c, _lib.TILE_ROWS, 4)[..., 2:4]            # salient words [TR,TC,128,2]
+        sh = torch.arange(32, device=self.device, dtype=torch.int32)
+        bits = ((pl.unsqueeze(-1) >> sh) & 1).to(torch.bool)                                     # [TR,TC,128,2,32]
+        sal = bits.permute(0, 2, 1, 3, 4).reshape(sz.n_pad, sz.k_pad)
+        return ~sal[: self.N, : self.K]
+
     # -- accounting --------------------------------------------------------------------------
     def packed_bytes(self) -> int:
         es = 4 if self.dtype == torch.float32 else 2

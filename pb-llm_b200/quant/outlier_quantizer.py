@@ -83,8 +83,10 @@ class BinaryXnorExceptOutliersLinear(_PackedBase):
         return w_sim, ~self.outlier_mask, -1
 
     def _key(self):
+        # identity and version of binary_scale, never its value: reading it would be a device->host sync per forward
+        # (and is illegal under CUDA-graph capture)
         bs = self.binary_scale
-        return super()._key() + (self.training, None if bs is None else float(bs))
+        return super()._key() + (self.training, None if bs is None else (id(bs), bs.data_ptr(), bs._version))
 
     def packed(self):
         if self._latent_dropped:

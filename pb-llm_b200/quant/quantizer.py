@@ -21,6 +21,11 @@ class BinaryInterface:
     """Reference quantizer.py:70-72."""
 
     def get_save_weight_dict(self):
+        if getattr(self, "_latent_dropped", False):
+            # pack(keep_latent=False) freed the latent weight: the reference's writer has nothing to write.
+            raise RuntimeError(f"{type(self).__name__}: the latent weight was dropped after packing "
+                               "(pack_model(keep_latent=False)); write this model with save_packed(), or keep the latent "
+                               "weights (pack_model(model, keep_latent=True)) to use save_bnn / state_dict")
         return {"weight": self.weight.data.half().cpu(), "bias": self.bias}
 
 
@@ -38,6 +43,7 @@ class _PackedBase(nn.Module, BinaryInterface):
             self.bias = None
         self._packed: Optional[PackedLinear] = None
         self._packed_key = None
+        self._packed_cast = {}       # autocast dtype -> PackedLinear of w_sim.to(dtype)
         self._latent_dropped = False
         self.global_name = None
         self.out_features, self.in_features = w.shape
@@ -67,6 +73,7 @@ class _PackedBase(nn.Module, BinaryInterface):
             self.weight = nn.Parameter(torch.empty(0, dtype=self.weight.dtype, device=self.weight.device),
                                        requires_grad=False)
             self._latent_dropped = True
+        self._packed_cast = {}
         return self._packed
 
     def packed(self) -> PackedLinear:
@@ -80,7 +87,28 @@ class _PackedBase(nn.Module, BinaryInterface):
         """w_sim as a dense tensor, reconstructed bit-exactly from the packed form."""
         return self.packed().unpack()
 
+    def packed_as(self, dtype: torch.dtype) -> PackedLinear:
+        """The layer packed from w_sim.to(dtype): what F.linear multiplies under torch.autocast (the cast of the
+        reference's materialised w_sim; casting is element-wise, so the two-level structure is kept)."""
+        p = self.packed()
+        if p.dtype == dtype:
+            return p
+        hit = self._packed_cast.get(dtype)
+        if hit is not None and hit[0] is p:
+            return hit[1]
+        with torch.no_grad():
+            w = p.unpack().to(dtype)
+            low = None if p.nnz == 0 else p.low_mask_dense()
+            q = PackedLinear.from_dense(w, p.bias, low_mask=low, groupsize=p.groupsize)
+        self._packed_cast[dtype] = (p, q)
+        return q
+
     def forward(self, x):
+        # F.linear under autocast (reference qat/run_qat.py:120 trains under bf16 autocast) casts x and w_sim to the
+        # autocast dtype and returns that dtype; without autocast mixed dtypes raise, like the reference.
+        if x.is_cuda and torch.is_autocast_enabled("cuda"):
+            dt = torch.get_autocast_dtype("cuda")
+            return self.packed_as(dt).forward(x.to(dt))
         return self.packed().forward(x)
 
     def to_regular_linear(self):

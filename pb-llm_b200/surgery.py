@@ -208,7 +208,7 @@ def load_packed(model: nn.Module, load_path: str, device=None):
         nn.Module.__init__(q)
         q.weight = nn.Parameter(torch.empty(0, dtype=dt, device=dev), requires_grad=False)
         q.bias = None if not info["bias"] else nn.Parameter(p.bias.to(dt), requires_grad=False)
-        q._packed, q._packed_key, q._latent_dropped = p, None, True
+        q._packed, q._packed_key, q._latent_dropped, q._packed_cast = p, None, True, {}
         q.global_name, q.out_features, q.in_features = name, info["N"], info["K"]
         for attr, val in (("outlier_mask", None), ("binary_scale", None), ("outlier_nbits", None), ("low_mask", None),
                           ("outlier_fraction", None), ("outlier_scale", 1), ("train_outlier", False), ("printed", False),

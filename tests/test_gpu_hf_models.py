@@ -88,3 +88,60 @@ def test_packed_checkpoint_roundtrip(tmp_path):
     with torch.no_grad():
         out = fresh(ids).logits
     assert torch.equal(out, ref)
+
+
+def test_autocast_matches_f_linear_under_autocast():
+    """Reference qat/run_qat.py:120 runs the modules under bf16 autocast: F.linear casts x and w_sim to the autocast
+    dtype. The drop-in must do the same instead of raising on the dtype mismatch."""
+    torch.manual_seed(1)
+    lin = torch.nn.Linear(256, 192, bias=True)
+    m = pb.BinaryXnorExceptOutliersLinear(lin.weight, lin.bias, 0.1).to(DEV).eval()      # fp32 module, as prepared for QAT
+    x = torch.randn(2, 5, 256, device=DEV)
+    with torch.no_grad():
+        w_sim = m.binarize_except_outliers()
+        for dt in (torch.bfloat16, torch.float16):
+            with torch.autocast("cuda", dtype=dt):
+                y = m(x)
+                ref = torch.nn.functional.linear(x, w_sim, m.bias)
+            assert y.dtype == dt == ref.dtype and y.shape == ref.shape
+            hi = torch.nn.functional.linear(x.to(dt).double(), w_sim.to(dt).double(), m.bias.double())
+            tol = 4e-3 if dt == torch.bfloat16 else 1e-3
+            assert float((y.double() - hi).abs().max() / hi.abs().max()) <= tol
+            assert float((ref.double() - hi).abs().max() / hi.abs().max()) <= 2 * tol      # cuBLAS itself, for scale
+        with pytest.raises(RuntimeError):
+            m(x.half())                                          # no autocast: mixed dtypes raise, like the reference
+
+
+def test_lazy_packed_forward_has_no_host_sync_and_is_graph_capturable():
+    """A BinaryXnorExceptOutliersLinear that still holds its latent weight (what replace_with_qlinear installs) must not
+    read binary_scale back to the host on every forward: that forward is captured into a CUDA graph here, which any
+    device->host sync would abort."""
+    torch.manual_seed(2)
+    lin = torch.nn.Linear(256, 128, bias=False).half()
+    m = pb.BinaryXnorExceptOutliersLinear(lin.weight, None, 0.1).to(DEV).eval()
+    x = torch.randn(4, 256, device=DEV, dtype=torch.float16)
+    with torch.no_grad():
+        y0 = m(x)                                                # first call packs (syncs are fine here)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            m(x)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                y1 = m(x)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(y0, y1)
+        key = m._key()
+        assert all(not isinstance(k, float) for k in key)
+
+
+def test_dropped_latent_refuses_the_reference_writer():
+    torch.manual_seed(3)
+    model = tiny_llama().to(DEV).half().eval()
+    pb.replace_with_qlinear(model, "xnor_outlier", 0.1)
+    pb.pack_model(model, keep_latent=True)
+    pb.surgery.get_bnn_weights(model)                            # latent kept: the reference's save path works
+    pb.pack_model(model, keep_latent=False)
+    with pytest.raises(RuntimeError, match="save_packed"):
+        pb.surgery.get_bnn_weights(model)

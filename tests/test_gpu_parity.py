@@ -441,38 +441,6 @@ def test_golden_gptqpb_fakequant_layers(tag):
     assert relmax(m2(t(g["x"])), g["y"]) <= 1e-3
 
 
-# ---- BiRealLinear: the XNOR-popcount layer ------------------------------------------------
-def test_golden_bireal_xnor_popcount():
-    g = load("quantizer_small")
-    m = pb.BiRealLinear(torch.from_numpy(g["W"]), torch.from_numpy(g["b"])).to(DEV)
-    y = m(t(g["x"]))
-    assert y.dtype == torch.float32 and y.shape == (2, 3, 96)
-    assert relmax(y, g["y_BiRealLinear"]) <= 2e-6                   # the executed reference; bias is dropped (:168)
-    assert relmax(m(t(g["x"]).half()), orc.bireal_forward(rounded(g["x"], torch.float16), g["W"])) <= 2e-6
-
-
-@pytest.mark.parametrize("xdtype", [torch.float16, torch.bfloat16, torch.float32])
-@pytest.mark.parametrize("N,K,M", [(128, 64, 1), (100, 70, 3), (300, 520, 8), (768, 768, 4), (4096, 4096, 8), (1024, 11008, 19)])
-def test_bireal_matches_oracle_and_popcount_identity(xdtype, N, K, M):
-    rs = np.random.RandomState(N + K + M)
-    W = (rs.standard_normal((N, K)) * 0.02).astype(np.float32)
-    W[rs.rand(N, K) < 0.01] = 0.0                                   # sign(0) = 0 weights
-    x = rounded(make_x(N + M, (M, K)), xdtype)
-    x[rs.rand(M, K) < 0.05] = 0.0                                   # and sign(0) = 0 activations (e.g. after ReLU)
-    m = pb.BiRealLinear(torch.from_numpy(W), None).to(DEV)
-    y = m(t(x, xdtype))
-    ref = orc.bireal_forward(x, W) if M * N * K <= 4e8 else \
-        (torch.sign(t(x)).double() @ (t(W).abs().mean(1, keepdim=True) * torch.sign(t(W))).double().t()).cpu().numpy()
-    assert relmax(y, ref) <= 2e-6
-    # the north star's literal formula: alpha_i * (2*popcount(xnor) - K) when no operand is zero
-    Wn, xn = np.where(W == 0, 0.01, W).astype(np.float32), np.where(x == 0, 1.0, x).astype(np.float32)
-    yn = pb.BiRealLinear(torch.from_numpy(Wn), None).to(DEV)(t(xn, xdtype)).cpu().numpy().astype(np.float64)
-    alpha = np.abs(Wn).astype(np.float64).mean(1)
-    agree = ((xn > 0)[:, None, :] == (Wn > 0)[None, :, :]).sum(-1) if M * N * K <= 2e7 else None
-    if agree is not None:
-        assert np.abs(yn - alpha[None, :] * (2.0 * agree - K)).max() <= 1e-6 * np.abs(yn).max()
-
-
 # ---- end-to-end host-buffer entry point ---------------------------------------------------------
 def test_forward_host_buffers():
     w, low = synth_wsim(256, 512, -1, torch.float16, 8)
@@ -737,26 +705,3 @@ def test_decode_kernel_activation_alignment_paths():
         ref = orc.linear(xv.float().cpu().numpy(), w)
         assert relmax(y, ref) <= 1e-3, off
         assert torch.equal(y, p.forward(xv.contiguous())), off       # same bits whatever the load path
-
-
-def test_bireal_stream_k_and_row_group_kernels_agree():
-    """pbl_bireal_forward_ws (stream-K XNOR kernel, zeroed reduction workspace) against pbl_bireal_forward (one CTA per
-    row group): same integer counts, fp32 folding in a different order; the stream-K result is repeatable bit for bit."""
-    lib = _lib.load()
-    for (N, K, M, zeros) in [(768, 768, 8, 0.0), (3072, 768, 5, 0.01), (130, 200, 19, 0.02), (4096, 4096, 8, 0.0)]:
-        rs = np.random.RandomState(N + K)
-        W = (rs.standard_normal((N, K)) * 0.02).astype(np.float32)
-        W[rs.rand(N, K) < zeros] = 0.0
-        m = pb.BiRealLinear(torch.from_numpy(W), None).to(DEV)
-        p = m.packed()
-        assert (p.sign_planes is not None) == (zeros == 0.0)
-        x = t(rounded(make_x(N + M, (M, K)), torch.float16), torch.float16)
-        y_new = p.bireal_forward(x)
-        assert int(lib.pbl_bireal_fixup_workspace(p.handle, M)) > 0
-        for _ in range(3):
-            assert torch.equal(y_new, p.bireal_forward(x))
-        y_old = torch.empty_like(y_new)
-        ws = torch.empty(p.bireal_workspace_bytes(M), dtype=torch.uint8, device=DEV)
-        rc = lib.pbl_bireal_forward(p.handle, x.data_ptr(), K, 0, y_old.data_ptr(), N, M, ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
-        assert rc == 0, _lib.last_error()
-        assert relmax(y_new, y_old.cpu().numpy()) <= 2e-6
