@@ -8,8 +8,10 @@
  *   gptq_pb/gptq.py:180-184       the fp16 nn.Linear that GPTQ-PB writes (format a10)
  * all of which end in  F.linear(x, w_sim, bias)  over a re-materialised dense w_sim
  * (quant/quantizer.py:86,193; quant/outlier_quantizer.py:105).  This library evaluates the same
- * y = x . w_sim^T + bias from a packed form of w_sim (1-bit sign plane + salient bitmap + packed
- * salient values + per-(row,group) {lo,hi}); unpack(pack(w_sim)) == w_sim bit-exactly.
+ * y = x . w_sim^T + bias from a packed form of w_sim; unpack(pack(w_sim)) == w_sim bit-exactly.  Two layouts:
+ *   fp16 / bf16 layers  "block stream": 1-bit sign plane in MMA-fragment order + one positioned 32-bit entry per salient
+ *                       weight + per-(row,group) {lo,hi}  (pbl_stream_*; the ONE resident copy every 16-bit kernel reads)
+ *   fp32 layers         "planes": 1-bit sign plane + salient bitmap + packed salient values + {lo,hi}  (pbl_pack_*)
  *
  * Conventions: plain pointers and sizes, no torch types, no exceptions across the ABI.
  * Every entry point returns PBL_OK (0) or a negative pbl_status; pbl_last_error() gives the
@@ -28,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PBL_ABI_VERSION 3
+#define PBL_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define PBL_API __attribute__((visibility("default")))
@@ -95,18 +97,27 @@ PBL_API int pbl_pack_vals(const void* w_sim, int64_t ldw, const void* planes, co
 
 /* ---- layer handle ------------------------------------------------------------------------ */
 
+#define PBL_LAYER_HAS_MID 1u /* some (row, group) has lo != -hi: reported by pbl_stream_count */
+
 typedef struct {
     int64_t N, K;        /* out_features, in_features of the replaced nn.Linear */
     int64_t groupsize;   /* as given to pbl_pack_sizes */
     int32_t dtype;       /* pbl_dtype */
-    int32_t reserved;
+    uint32_t flags;      /* PBL_LAYER_* (block-stream layers) */
+    const void* affine;  /* device float2 [n_pad][groups] */
+    const void* bias;    /* device float32 [N] or NULL (bias added inside, as F.linear does) */
+    /* -- planes layout (dtype PBL_F32; NULL for 16-bit layers) -- */
     const void* planes;  /* device, 16 B aligned */
     const void* vptr;    /* device */
     const void* vals;    /* device, dtype, 16 B aligned, >= nnz + 8 elements */
-    const void* affine;  /* device float2 [n_pad][groups] */
-    const void* bias;    /* device float32 [N] or NULL (bias added inside, as F.linear does) */
     const void* sign_planes; /* optional, device uint2 [tiles_r][tiles_c][128] = the sign words of `planes` only;
                               * may be given iff nnz == 0 (pure binary layer): halves the bytes pbl_bireal_forward streams */
+    /* -- block-stream layout (dtype PBL_F16 / PBL_BF16; NULL for fp32 layers) -- */
+    const void* fsign;   /* device uint2 [blocks][32], 16 B aligned */
+    const void* eptr;    /* device u32 [blocks + 1] */
+    const void* ent;     /* device u32 [4 * eptr[blocks]], 16 B aligned (at least 16 bytes) */
+    const void* exc;     /* device u32 [n_exc][2] or NULL */
+    int64_t n_exc;
 } pbl_layer_desc;
 
 typedef struct pbl_layer pbl_layer; /* opaque; borrows the descriptor's device pointers */
@@ -125,10 +136,10 @@ PBL_API int pbl_unpack(const pbl_layer* layer, void* w_out, int64_t ldw, void* s
  * Replaces F.linear(x, w_sim, bias) at quant/quantizer.py:86,193 and
  * quant/outlier_quantizer.py:105.  x: device [M][ldx], y: device [M][ldy] (row-major, dtype).
  * M = product of the leading dims of the reference's x[..., K].  M == 0 is a no-op.
- * For fp16/bf16 and M > 128 the weight is first expanded into a transient dense scratch of
- * 2*n_pad*k_pad bytes taken from (and returned to) the device's stream-ordered memory pool on `stream`
- * (cudaMallocAsync / cudaFreeAsync: no synchronisation, CUDA-graph capturable); PBL_TWOPHASE=0 selects the
- * fused kernels that need no scratch. */
+ * fp16 / bf16 layers: calls of up to PBL_DECODE_MAX_M tokens (default 64) run the decode kernel in passes of 16 tokens;
+ * larger calls first expand the weight into a transient dense scratch of 2*n_pad*k_pad bytes taken from (and returned
+ * to) the device's stream-ordered memory pool on `stream` (cudaMallocAsync / cudaFreeAsync: no synchronisation,
+ * CUDA-graph capturable) and run the tcgen05 GEMM over it.  fp32 layers run the CUDA-core bit-plane kernel. */
 PBL_API int pbl_linear_forward(const pbl_layer* layer, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M,
                        void* stream);
 
@@ -140,22 +151,28 @@ PBL_API size_t pbl_forward_host_workspace(const pbl_layer* layer, int64_t M);
 PBL_API int pbl_linear_forward_host(const pbl_layer* layer, const void* x_host, void* y_host, int64_t M, void* workspace,
                             void* stream);
 
-/* ---- decode index (optional, fp16 / bf16 layers): a second, row-group-major view of the packed layer with an
- *      explicit tile position per salient entry, built once from the packed buffers.  With it attached,
- *      pbl_linear_forward[_ws] routes calls of M <= 16 tokens (the per-token step of generation, where the
- *      reference's F.linear re-reads the whole dense weight: quant/quantizer.py:86,193, outlier_quantizer.py:105)
- *      to the decode kernel.  Sizes: dsign = blocks*32*8 bytes, eptr = (blocks+1)*4 bytes, ent = 16 bytes per
- *      unit, units = eptr[blocks] after pbl_decode_index_count (read it back to size `ent`). ---- */
+/* ---- block-stream layout of fp16 / bf16 layers (csrc/pbllm_stream.cuh): blocks of 32 rows x 64 columns in
+ *      row-group-major order.  It is what the decode kernel streams for calls of a few tokens (the per-token step of
+ *      generation, where the reference's F.linear re-reads the whole dense weight: quant/quantizer.py:86,193,
+ *      outlier_quantizer.py:105) and what pbl_unpack / the prefill expansion read back.  Packing (one-time):
+ *        pbl_pack_affine -> pbl_stream_count (eptr; read back eptr[blocks] = units and stats) -> pbl_stream_fill.
+ *      Sizes: fsign = blocks*32*8 bytes, eptr = (blocks+1)*4 bytes, ent = 16 bytes per unit, exc = 8 bytes per exception.
+ *      pbl_stream_count rewrites `affine` in place for single-level (row, group)s that hold salient weights ({mid-1, mid+1}:
+ *      all their positions become entries).  stats (device u32[4]): [0] exceptions, [1] PBL_LAYER_HAS_MID flag, [2] exceptions written by pbl_stream_fill. ---- */
 typedef struct {
     int64_t blocks;      /* (n_pad/32) * tiles_c blocks of 32 rows x 64 columns */
-    size_t dsign_bytes;  /* uint2 [blocks][32] sign words */
+    size_t fsign_bytes;  /* uint2 [blocks][32] fragment-ordered sign words */
     size_t eptr_bytes;   /* u32 [blocks + 1] entry offsets in 16-byte units */
-} pbl_decode_sizes;
-PBL_API int pbl_decode_index_sizes(const pbl_layer* layer, pbl_decode_sizes* out);
-PBL_API int pbl_decode_index_count(const pbl_layer* layer, void* eptr_out, void* stream);
-PBL_API int pbl_decode_index_fill(const pbl_layer* layer, const void* eptr, void* dsign_out, void* ent_out, void* stream);
-/* Borrow the three device buffers (16 B aligned); NULLs detach. */
-PBL_API int pbl_layer_attach_decode_index(pbl_layer* layer, const void* dsign, const void* eptr, const void* ent);
+} pbl_stream_sizes;
+PBL_API int pbl_stream_layout(int64_t N, int64_t K, int64_t groupsize, int dtype, pbl_stream_sizes* out);
+PBL_API int pbl_stream_count(const void* w_sim, int64_t ldw, const uint8_t* low_mask, void* affine, int64_t N, int64_t K,
+                             int64_t groupsize, int dtype, void* eptr_out, void* stats_out, void* stream);
+PBL_API int pbl_stream_fill(const void* w_sim, int64_t ldw, const uint8_t* low_mask, const void* affine, int64_t N, int64_t K,
+                            int64_t groupsize, int dtype, const void* eptr, void* fsign_out, void* ent_out, void* exc_out,
+                            int64_t exc_capacity, void* stats, void* stream);
+/* Host-only: where position (r, c) of a block lives -- out4 = {owner lane, sign word, sign bit, correction-tile slot}
+ * (tests/test_stream_layout.py checks the fragment mapping against mma.sync's documented layout on the CPU). */
+PBL_API int pbl_stream_position(int r, int c, uint32_t* out4);
 
 /* pbl_linear_forward with a caller-owned device workspace for the decode kernel's cross-CTA reduction:
  * >= pbl_decode_workspace_bytes(layer, M) bytes, 16 B aligned, ZERO-INITIALISED ONCE by the caller (the kernel
@@ -194,10 +211,9 @@ PBL_API size_t pbl_bireal_fixup_workspace(const pbl_layer* layer, int64_t M);
 PBL_API int pbl_bireal_forward_ws(const pbl_layer* layer, const void* x, int64_t ldx, int x_dtype, float* y, int64_t ldy,
                                   int64_t M, void* workspace, void* fixup_workspace, size_t fixup_workspace_bytes, void* stream);
 
-/* Which kernel pbl_linear_forward would launch for this (layer, M): 0 = CUDA-core bit-plane
- * kernel (fp32 I/O), 1 = tcgen05 bit-plane GEMM (M above PBL_SKINNY_MAX_M, default 16),
- * 2 = mma.sync bit-plane skinny kernel (decode without a decode index), 3 = tcgen05 split-K cluster kernel
- * (M <= 128), 4 = decode kernel (M <= 16, decode index attached).  PBL_FORCE_KERNEL=0|1|2|3|4 overrides (tests). */
+/* Which kernel pbl_linear_forward would launch for this (layer, M): 0 = CUDA-core bit-plane kernel (fp32 layers),
+ * 1 = two-phase prefill (expansion + tcgen05 GEMM; fp16 / bf16 layers, M above PBL_DECODE_MAX_M, default 64),
+ * 4 = decode kernel.  PBL_FORCE_KERNEL=0|1|4 overrides (tests). */
 PBL_API int pbl_select_kernel(const pbl_layer* layer, int64_t M);
 
 /* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */

@@ -19,12 +19,13 @@ class PblSizes(C.Structure):
 
 class PblLayerDesc(C.Structure):
     _fields_ = [("N", C.c_int64), ("K", C.c_int64), ("groupsize", C.c_int64), ("dtype", C.c_int32),
-                ("reserved", C.c_int32), ("planes", C.c_void_p), ("vptr", C.c_void_p), ("vals", C.c_void_p),
-                ("affine", C.c_void_p), ("bias", C.c_void_p), ("sign_planes", C.c_void_p)]
+                ("flags", C.c_uint32), ("affine", C.c_void_p), ("bias", C.c_void_p),
+                ("planes", C.c_void_p), ("vptr", C.c_void_p), ("vals", C.c_void_p), ("sign_planes", C.c_void_p),
+                ("fsign", C.c_void_p), ("eptr", C.c_void_p), ("ent", C.c_void_p), ("exc", C.c_void_p), ("n_exc", C.c_int64)]
 
 
-class PblDecodeSizes(C.Structure):
-    _fields_ = [("blocks", C.c_int64), ("dsign_bytes", C.c_size_t), ("eptr_bytes", C.c_size_t)]
+class PblStreamSizes(C.Structure):
+    _fields_ = [("blocks", C.c_int64), ("fsign_bytes", C.c_size_t), ("eptr_bytes", C.c_size_t)]
 
 
 # name -> (restype, argtypes): every symbol include/pbllm.h declares
@@ -43,10 +44,12 @@ SYMBOLS = {
                                      C.c_void_p]),
     "pbl_linear_forward_ws": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
                                         C.c_void_p, C.c_size_t, C.c_void_p]),
-    "pbl_decode_index_sizes": (C.c_int, [C.c_void_p, C.POINTER(PblDecodeSizes)]),
-    "pbl_decode_index_count": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
-    "pbl_decode_index_fill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "pbl_layer_attach_decode_index": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pbl_stream_layout": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(PblStreamSizes)]),
+    "pbl_stream_count": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pbl_stream_fill": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "pbl_stream_position": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_uint32)]),
     "pbl_decode_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64]),
     "pbl_decode_set_trace": (None, [C.c_void_p, C.c_size_t]),
     "pbl_decode_plan": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_uint32)]),
@@ -92,7 +95,7 @@ def load():
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.pbl_abi_version() != 3:
+    if lib.pbl_abi_version() != 4:
         raise RuntimeError("libpbllm.so ABI version mismatch")
     _lib = lib
     return lib

@@ -8,12 +8,7 @@
 #include <cstring>
 #include <new>
 
-#include "pbllm_common.cuh"
-
-namespace pbl {
-int launch_gemm_splitk(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s);
-bool gemm_splitk_supported(const Layer& L, const void* x, int64_t ldx, const void* y, int64_t ldy, int64_t M);
-}  // namespace pbl
+#include "pbllm_stream.cuh"
 
 namespace pbl {
 
@@ -145,8 +140,16 @@ int pbl_layer_create(const pbl_layer_desc* d, pbl_layer** out) {
     pbl_sizes sz;
     int rc = sizes_impl(d->N, d->K, d->groupsize, d->dtype, &sz);
     if (rc) return rc;
-    if (!d->planes || !d->vptr || !d->vals || !d->affine) { set_error("pbl_layer_create: null packed buffer"); return PBL_ERR_NULL; }
-    if (!aligned16(d->planes) || !aligned16(d->vals)) { set_error("pbl_layer_create: planes/vals must be 16 B aligned"); return PBL_ERR_ALIGN; }
+    if (!d->affine) { set_error("pbl_layer_create: null affine table"); return PBL_ERR_NULL; }
+    const bool stream_layout = d->dtype != PBL_F32;
+    if (stream_layout) {       // fp16 / bf16: block-stream layout
+        if (!d->fsign || !d->eptr || !d->ent) { set_error("pbl_layer_create: fp16 / bf16 layers need fsign / eptr / ent (pbl_stream_*)"); return PBL_ERR_NULL; }
+        if (!aligned16(d->fsign) || !aligned16(d->ent)) { set_error("pbl_layer_create: fsign/ent must be 16 B aligned"); return PBL_ERR_ALIGN; }
+        if (d->n_exc < 0 || (d->n_exc > 0 && !d->exc)) { set_error("pbl_layer_create: n_exc without an exception list"); return PBL_ERR_NULL; }
+    } else {                   // fp32: planes layout
+        if (!d->planes || !d->vptr || !d->vals) { set_error("pbl_layer_create: fp32 layers need planes / vptr / vals (pbl_pack_*)"); return PBL_ERR_NULL; }
+        if (!aligned16(d->planes) || !aligned16(d->vals)) { set_error("pbl_layer_create: planes/vals must be 16 B aligned"); return PBL_ERR_ALIGN; }
+    }
     Layer* L = new (std::nothrow) Layer();
     if (!L) { set_error("out of host memory"); return PBL_ERR_CUDA; }
     L->N = d->N; L->K = d->K;
@@ -154,10 +157,16 @@ int pbl_layer_create(const pbl_layer_desc* d, pbl_layer** out) {
     L->dtype = d->dtype;
     L->n_pad = sz.n_pad; L->k_pad = sz.k_pad; L->tiles_r = sz.tiles_r; L->tiles_c = sz.tiles_c; L->groups = sz.groups;
     L->tiles_per_group = (sz.groups == 1) ? (int)sz.tiles_c : (int)(L->groupsize / kTileCols);
-    L->planes = (const uint4*)d->planes; L->vptr = (const uint32_t*)d->vptr; L->vals = d->vals;
     L->affine = (const float2*)d->affine; L->bias = (const float*)d->bias;
-    L->sign_planes = (const uint2*)d->sign_planes;
-    L->dsign = nullptr; L->eptr = nullptr; L->ent = nullptr;
+    L->planes = nullptr; L->vptr = nullptr; L->vals = nullptr; L->sign_planes = nullptr;
+    L->fsign = nullptr; L->eptr = nullptr; L->ent = nullptr; L->exc = nullptr; L->n_exc = 0; L->flags = d->flags;
+    if (stream_layout) {
+        L->fsign = (const uint2*)d->fsign; L->eptr = (const uint32_t*)d->eptr; L->ent = (const uint32_t*)d->ent;
+        L->exc = (const uint32_t*)d->exc; L->n_exc = d->n_exc;
+    } else {
+        L->planes = (const uint4*)d->planes; L->vptr = (const uint32_t*)d->vptr; L->vals = d->vals;
+        L->sign_planes = (const uint2*)d->sign_planes;
+    }
     *out = reinterpret_cast<pbl_layer*>(L);
     return PBL_OK;
 }
@@ -170,6 +179,7 @@ int pbl_unpack(const pbl_layer* layer, void* w_out, int64_t ldw, void* stream) {
     if (ldw < L.K) { set_error("pbl_unpack: ldw < K"); return PBL_ERR_SHAPE; }
     int rc = device_check_impl();
     if (rc) return rc;
+    if (L.fsign) return launch_stream_unpack(L, w_out, ldw, L.N, L.K, (cudaStream_t)stream);
     return launch_unpack(L, w_out, ldw, (cudaStream_t)stream);
 }
 
@@ -179,36 +189,28 @@ static int forced_kernel() {
     return atoi(e);
 }
 
-static int skinny_max_m() {
-    const char* e = getenv("PBL_SKINNY_MAX_M");
-    if (e && *e) return atoi(e);
-    return 16;
+static int decode_max_m() {   // calls of up to this many tokens run the decode kernel (in passes of 16)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PBL_DECODE_MAX_M");
+        v = (e && *e) ? atoi(e) : 64;
+        if (v < 1) v = 1;
+    }
+    return v;
 }
 
-static int splitk_max_m() {   // M up to which the split-K cluster kernel is preferred (0 disables it)
-    const char* e = getenv("PBL_SPLITK_MAX_M");
-    if (e && *e) return atoi(e);
-    return 128;
-}
-
-// 0 = CUDA-core bit-plane kernel, 1 = tcgen05 GEMM (single-CTA / CTA-pair), 2 = mma.sync skinny kernel,
-// 3 = tcgen05 split-K cluster kernel (M <= 128), 4 = decode kernel (decode index attached); -1 = forced kernel unsupported
+// 0 = CUDA-core bit-plane kernel (fp32 layers), 1 = two-phase prefill (expansion + tcgen05 GEMM), 4 = decode kernel;
+// -1 = forced kernel unsupported
 static int select_impl(const Layer& L, const void* x, int64_t ldx, const void* y, int64_t ldy, int64_t M) {
-    const bool tc_ok = gemm_tc_supported(L, x, ldx, y, ldy, M);
-    const bool sk_ok = skinny_supported(L, M);
-    const bool ck_ok = gemm_splitk_supported(L, x, ldx, y, ldy, M);
     const int f = forced_kernel();
-    if (f == 0) return 0;
+    if (!L.fsign) return (f < 0 || f == 0) ? 0 : -1;                     // fp32 layer: planes layout, CUDA cores
+    const bool tc_ok = gemm_twophase_supported(L, x, ldx, y, ldy, M);
+    const bool dk_ok = decode_supported(L, ldx, M);
     if (f == 1) return tc_ok ? 1 : -1;
-    if (f == 2) return sk_ok ? 2 : -1;
-    if (f == 3) return ck_ok ? 3 : -1;
-    if (f == 4) return decode_supported(L, ldx, M) ? 4 : -1;
-    if (!sk_ok) return 0;                       // fp32 I/O: CUDA cores
-    if (M <= skinny_max_m() && decode_supported(L, ldx, M)) return 4;   // decode: positioned-entry kernel, stream-K over warps
-    if (M <= skinny_max_m()) return 2;          // decode: mma.sync skinny kernel (measured faster than split-K up to 16 tokens)
-    if (ck_ok && M <= splitk_max_m()) return 3; // short prompts: split-K cluster kernel (2x the single-CTA GEMM at M = 64)
-    if (!tc_ok) return 2;
-    return 1;
+    if (f == 4) return dk_ok ? 4 : -1;
+    if (f >= 0) return -1;
+    if ((M <= decode_max_m() || !tc_ok) && dk_ok) return 4;
+    return tc_ok ? 1 : -1;
 }
 
 int pbl_select_kernel(const pbl_layer* layer, int64_t M) {
@@ -237,51 +239,66 @@ int pbl_linear_forward_ws(const pbl_layer* layer, const void* x, int64_t ldx, vo
     int rc = device_check_impl();
     if (rc) return rc;
     const int k = select_impl(L, x, ldx, y, ldy, M);
-    if (k < 0) { set_error("PBL_FORCE_KERNEL names a kernel that does not support this call"); return PBL_ERR_UNSUPPORTED; }
-    if (k == 1) return launch_gemm_tc(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
-    if (k == 2) return launch_skinny(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
-    if (k == 3) return launch_gemm_splitk(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
+    if (k < 0) { set_error("no kernel supports this call (PBL_FORCE_KERNEL, or activations too large for 32-bit offsets)"); return PBL_ERR_UNSUPPORTED; }
+    if (k == 1) return launch_gemm_twophase(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
     if (k == 4) return launch_decode(L, x, ldx, y, ldy, M, workspace, workspace_bytes, (cudaStream_t)stream);
     return launch_gemv(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
 }
 
-int pbl_decode_index_sizes(const pbl_layer* layer, pbl_decode_sizes* out) {
-    if (!layer || !out) { set_error("pbl_decode_index_sizes: null pointer"); return PBL_ERR_NULL; }
-    const Layer& L = *reinterpret_cast<const Layer*>(layer);
-    if (L.dtype != PBL_F16 && L.dtype != PBL_BF16) { set_error("the decode index needs an fp16 / bf16 layer"); return PBL_ERR_DTYPE; }
-    out->blocks = L.tiles_r * kRgPerTile * L.tiles_c;
-    out->dsign_bytes = (size_t)out->blocks * kRgRows * sizeof(uint2);
+int pbl_stream_layout(int64_t N, int64_t K, int64_t groupsize, int dtype, pbl_stream_sizes* out) {
+    if (!out) { set_error("pbl_stream_layout: out is NULL"); return PBL_ERR_NULL; }
+    if (dtype != PBL_F16 && dtype != PBL_BF16) { set_error("the block-stream layout holds fp16 / bf16 layers"); return PBL_ERR_DTYPE; }
+    pbl_sizes sz;
+    int rc = sizes_impl(N, K, groupsize, dtype, &sz);
+    if (rc) return rc;
+    out->blocks = sz.tiles_r * kRgPerTile * sz.tiles_c;
+    out->fsign_bytes = (size_t)out->blocks * kRgRows * sizeof(uint2);
     out->eptr_bytes = (size_t)(out->blocks + 1) * sizeof(uint32_t);
     return PBL_OK;
 }
 
-int pbl_decode_index_count(const pbl_layer* layer, void* eptr_out, void* stream) {
-    if (!layer || !eptr_out) { set_error("pbl_decode_index_count: null pointer"); return PBL_ERR_NULL; }
-    const Layer& L = *reinterpret_cast<const Layer*>(layer);
-    if (L.dtype != PBL_F16 && L.dtype != PBL_BF16) { set_error("the decode index needs an fp16 / bf16 layer"); return PBL_ERR_DTYPE; }
-    int rc = device_check_impl();
+static int stream_args(const char* who, const void* w, int64_t ldw, const void* affine, int64_t N, int64_t K, int64_t groupsize,
+                       int dtype, pbl_sizes* sz, int* tpg) {
+    if (dtype != PBL_F16 && dtype != PBL_BF16) { set_error("%s: the block-stream layout holds fp16 / bf16 layers", who); return PBL_ERR_DTYPE; }
+    int rc = sizes_impl(N, K, groupsize, dtype, sz);
     if (rc) return rc;
-    return launch_decode_index_count(L, (uint32_t*)eptr_out, (cudaStream_t)stream);
+    if (!w || !affine) { set_error("%s: null pointer", who); return PBL_ERR_NULL; }
+    if (ldw < K) { set_error("%s: ldw %lld < K %lld", who, (long long)ldw, (long long)K); return PBL_ERR_SHAPE; }
+    const int64_t gs = (groupsize <= 0 || groupsize >= K) ? K : groupsize;
+    *tpg = (sz->groups == 1) ? (int)sz->tiles_c : (int)(gs / kTileCols);
+    return device_check_impl();
 }
 
-int pbl_decode_index_fill(const pbl_layer* layer, const void* eptr, void* dsign_out, void* ent_out, void* stream) {
-    if (!layer || !eptr || !dsign_out || !ent_out) { set_error("pbl_decode_index_fill: null pointer"); return PBL_ERR_NULL; }
-    const Layer& L = *reinterpret_cast<const Layer*>(layer);
-    if (L.dtype != PBL_F16 && L.dtype != PBL_BF16) { set_error("the decode index needs an fp16 / bf16 layer"); return PBL_ERR_DTYPE; }
-    if (!aligned16(dsign_out) || !aligned16(ent_out)) { set_error("pbl_decode_index_fill: dsign/ent must be 16 B aligned"); return PBL_ERR_ALIGN; }
-    int rc = device_check_impl();
+int pbl_stream_count(const void* w_sim, int64_t ldw, const uint8_t* low_mask, void* affine, int64_t N, int64_t K,
+                     int64_t groupsize, int dtype, void* eptr_out, void* stats_out, void* stream) {
+    pbl_sizes sz;
+    int tpg = 0;
+    int rc = stream_args("pbl_stream_count", w_sim, ldw, affine, N, K, groupsize, dtype, &sz, &tpg);
     if (rc) return rc;
-    return launch_decode_index_fill(L, (const uint32_t*)eptr, (uint2*)dsign_out, (uint32_t*)ent_out, (cudaStream_t)stream);
+    if (!eptr_out || !stats_out) { set_error("pbl_stream_count: null output"); return PBL_ERR_NULL; }
+    return launch_stream_count(w_sim, ldw, low_mask, (float2*)affine, N, K, dtype, sz, tpg, (uint32_t*)eptr_out,
+                               (uint32_t*)stats_out, (cudaStream_t)stream);
 }
 
-int pbl_layer_attach_decode_index(pbl_layer* layer, const void* dsign, const void* eptr, const void* ent) {
-    if (!layer) { set_error("pbl_layer_attach_decode_index: null layer"); return PBL_ERR_NULL; }
-    Layer& L = *reinterpret_cast<Layer*>(layer);
-    if (!dsign && !eptr && !ent) { L.dsign = nullptr; L.eptr = nullptr; L.ent = nullptr; return PBL_OK; }
-    if (!dsign || !eptr || !ent) { set_error("pbl_layer_attach_decode_index: all three buffers or none"); return PBL_ERR_NULL; }
-    if (L.dtype != PBL_F16 && L.dtype != PBL_BF16) { set_error("the decode index needs an fp16 / bf16 layer"); return PBL_ERR_DTYPE; }
-    if (!aligned16(dsign) || !aligned16(ent)) { set_error("pbl_layer_attach_decode_index: dsign/ent must be 16 B aligned"); return PBL_ERR_ALIGN; }
-    L.dsign = (const uint2*)dsign; L.eptr = (const uint32_t*)eptr; L.ent = (const uint32_t*)ent;
+int pbl_stream_fill(const void* w_sim, int64_t ldw, const uint8_t* low_mask, const void* affine, int64_t N, int64_t K,
+                    int64_t groupsize, int dtype, const void* eptr, void* fsign_out, void* ent_out, void* exc_out,
+                    int64_t exc_capacity, void* stats, void* stream) {
+    pbl_sizes sz;
+    int tpg = 0;
+    int rc = stream_args("pbl_stream_fill", w_sim, ldw, affine, N, K, groupsize, dtype, &sz, &tpg);
+    if (rc) return rc;
+    if (!eptr || !fsign_out || !ent_out || !stats) { set_error("pbl_stream_fill: null pointer"); return PBL_ERR_NULL; }
+    if (exc_capacity < 0 || (exc_capacity > 0 && !exc_out)) { set_error("pbl_stream_fill: exception capacity without a buffer"); return PBL_ERR_NULL; }
+    if (!aligned16(fsign_out) || !aligned16(ent_out)) { set_error("pbl_stream_fill: fsign/ent must be 16 B aligned"); return PBL_ERR_ALIGN; }
+    return launch_stream_fill(w_sim, ldw, low_mask, (const float2*)affine, N, K, dtype, sz, tpg, (const uint32_t*)eptr, (uint2*)fsign_out,
+                              (uint32_t*)ent_out, (uint32_t*)exc_out, (uint32_t)exc_capacity, (uint32_t*)stats, (cudaStream_t)stream);
+}
+
+int pbl_stream_position(int r, int c, uint32_t* out4) {
+    if (!out4) { set_error("pbl_stream_position: out is NULL"); return PBL_ERR_NULL; }
+    if (r < 0 || r >= kRgRows || c < 0 || c >= kTileCols) { set_error("pbl_stream_position: (r, c) outside the 32 x 64 block"); return PBL_ERR_SHAPE; }
+    st::sign_pos((uint32_t)r, (uint32_t)c, out4[0], out4[1], out4[2]);
+    out4[3] = st::tile_slot((uint32_t)r, (uint32_t)c);
     return PBL_OK;
 }
 
@@ -318,6 +335,7 @@ int pbl_bireal_forward_ws(const pbl_layer* layer, const void* x, int64_t ldx, in
                           void* workspace, void* fixup_ws, size_t fixup_bytes, void* stream) {
     if (!layer) { set_error("pbl_bireal_forward: null layer"); return PBL_ERR_NULL; }
     const Layer& L = *reinterpret_cast<const Layer*>(layer);
+    if (!L.planes) { set_error("pbl_bireal_forward needs a planes-layout (fp32) layer, as BiRealLinear packs"); return PBL_ERR_DTYPE; }
     if (M < 0 || M > 65535LL * 8) { set_error("pbl_bireal_forward: bad M=%lld", (long long)M); return PBL_ERR_SHAPE; }
     if (M == 0) return PBL_OK;
     if (!x || !y || !workspace) { set_error("pbl_bireal_forward: null pointer"); return PBL_ERR_NULL; }

@@ -26,10 +26,14 @@ struct Layer {  // the opaque pbl_layer
     const float2* affine; // [n_pad][groups] {lo, hi}
     const float* bias;
     const uint2* sign_planes;  // optional compact sign-only planes (nnz == 0 layers)
-    // optional decode index (pbl_decode_index_*): row-group-major sign words, entry offsets, positioned salient entries
-    const uint2* dsign;
+    // block-stream layout (fp16 / bf16 layers; pbllm_stream.cuh): fragment-ordered sign words, entry offsets, salient
+    // entries {slot, k, correction}, exception list; flags = PBL_LAYER_*
+    const uint2* fsign;
     const uint32_t* eptr;
     const uint32_t* ent;
+    const uint32_t* exc;
+    int64_t n_exc;
+    uint32_t flags;
 };
 
 void set_error(const char* fmt, ...);
@@ -66,12 +70,14 @@ int launch_pack_vals(const void* w, int64_t ldw, const uint4* planes, const uint
                      int dtype, void* vals, const pbl_sizes& sz, cudaStream_t s);
 int launch_unpack(const Layer& L, void* w_out, int64_t ldw, cudaStream_t s);
 int launch_gemv(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s);
-int launch_gemm_tc(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s);
-bool gemm_tc_supported(const Layer& L, const void* x, int64_t ldx, const void* y, int64_t ldy, int64_t M);
-int launch_skinny(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s);
-bool skinny_supported(const Layer& L, int64_t M);
-int launch_decode_index_count(const Layer& L, uint32_t* eptr, cudaStream_t s);
-int launch_decode_index_fill(const Layer& L, const uint32_t* eptr, uint2* dsign, uint32_t* ent, cudaStream_t s);
+int launch_stream_count(const void* w, int64_t ldw, const uint8_t* low_mask, float2* affine, int64_t N, int64_t K, int dtype,
+                        const pbl_sizes& sz, int tiles_per_group, uint32_t* eptr, uint32_t* stats, cudaStream_t s);
+int launch_stream_fill(const void* w, int64_t ldw, const uint8_t* low_mask, const float2* affine, int64_t N, int64_t K, int dtype,
+                       const pbl_sizes& sz, int tiles_per_group, const uint32_t* eptr, uint2* fsign, uint32_t* ent, uint32_t* exc,
+                       uint32_t exc_cap, uint32_t* stats, cudaStream_t s);
+int launch_stream_unpack(const Layer& L, void* out, int64_t ldw, int64_t n_rows, int64_t n_cols, cudaStream_t s);
+int launch_gemm_twophase(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s);
+bool gemm_twophase_supported(const Layer& L, const void* x, int64_t ldx, const void* y, int64_t ldy, int64_t M);
 bool decode_supported(const Layer& L, int64_t ldx, int64_t M);
 size_t decode_workspace_bytes(const Layer& L, int64_t M);
 void decode_set_trace(void* buf, size_t bytes);

@@ -1,29 +1,32 @@
-// Decode kernel (M <= 16 tokens per call, fp16 / bf16): the HBM-bound regime of the bit-plane forward.
+// Decode kernel (M <= 16 tokens per pass, fp16 / bf16): the HBM-bound regime of the bit-plane forward.
 //
-// Same math as every other kernel of the library (y = x . w_sim^T + b, the EXACT w_sim tile rebuilt in shared
-// memory and multiplied on the tensor cores with fp32 accumulation), reorganised around what bounds a
-// 2-microsecond kernel: instructions per weight, dependent DRAM round trips, and SM load balance.
+//   y[m][i] = sum_g ( mid_ig * sum_{j in g} x[m][j] + half_ig * sum_{j in g} t_ij x[m][j] ) + b_i
 //
-//  * decode index (built once at pack time, pbl_decode_index_*): the layer in ROW-GROUP-MAJOR block order --
-//    block (rg, kb) = 32 output rows x 64 input columns, linear id rg*tiles_c + kb:
-//      dsign uint2 [blocks][32]        the sign words of the block's rows (1 bit / weight)
-//      eptr  u32   [blocks + 1]        offset of each block's salient entries, in 16-byte units
-//      ent   u32   [..]                one entry per salient weight: (byte offset in the 4 KB swizzled tile) << 16
-//                                      | the value's 16 bits; blocks padded to 4 entries with copies of their last
-//                                      entry (an idempotent store).
-//    With explicit positions the salient patch is lane-balanced: entry e of a block is handled by lane e/4 % 32,
-//    3 instructions per entry, no per-row bit walking, no warp scan, no divergence.
-//  * warp-granular stream-K: the blocks of the layer are dealt out in contiguous, equal (+-1) runs to the
-//    warps of a fixed grid (3 CTAs per SM), so every SM gets the same number of blocks whatever N and K are.
-//    A warp's run covers at most two partial row groups (head / tail) plus whole ones; partials are reduced
-//    across the warps of the CTA in shared memory, and across CTAs through a small global workspace: each
-//    contributor parks {partial, valid tag} with one 64-bit store per output (no fence, no counter), the last
-//    contributor polls the slots and sums them in CTA order, so the result is deterministic.
-//  * every weight-side load of a warp's first blocks is issued before griddepcontrol.wait: under programmatic
-//    dependent launch the packed stream of layer i+1 is in flight while layer i still computes.
+// with t_ij = +-1 at binarized positions (the sign plane; mid = (lo+hi)/2, half = (hi-lo)/2 of the row's two levels) and
+// t_ij = tau_ij = (w_ij - mid)/half at salient positions (block-stream layout, pbllm_stream.cuh) -- the same w_sim as every
+// other kernel of the library, summed in fp32 on the tensor cores.  What bounds a 2-microsecond kernel is instructions and
+// shared-memory wavefronts per weight:
+//
+//  * ONE instruction pair per two weights.  Each warp keeps a 4 KB tile that holds +1.0 everywhere; a block's salient
+//    entries are patched into it (one LEA + one STS.U16 each, lane-balanced, bank-spread at pack time).  The sign words are
+//    stored in MMA-fragment order, so after ldmatrix a lane turns its 64 sign bits and the tile words into the 32 A-fragment
+//    registers of the block's eight mma.sync.m16n8k16 with one shift + one LOP3 each: ((w << rho) & 0x80008000) ^ tile.
+//    Nothing of the 90 % binarized weights is ever written to shared memory; the entries are then reset to +1.0 (one STS
+//    each).  Shared-memory traffic per weight drops from write + patch + read of the full tile to read + 2 x patch.
+//  * the levels are applied to the fp32 accumulators when a (row group, group) segment ends; sum_j x[m][j] comes from the
+//    tensor cores too (an all-ones A fragment), and only for layers that have an asymmetric level pair.
+//  * activations never touch shared memory: lane (token g, segment t) loads its 16 consecutive activations with one
+//    256-bit load; the column permutation of the layout makes those registers the B fragments.  They are loaded one block
+//    ahead into a second register set.
+//  * warp-granular stream-K (unchanged): the blocks of the layer are dealt out in contiguous, equal (+-1) runs to the warps
+//    of a fixed grid, partial row groups are reduced across the CTA's warps in shared memory and across CTAs through a
+//    small zeroed workspace with tagged 64-bit slots, summed in CTA order (deterministic).
+//  * every weight-side load of a warp's first blocks is issued before griddepcontrol.wait: under programmatic dependent
+//    launch the packed stream of layer i+1 is in flight while layer i still computes.
 #include <cstdlib>
 #include <type_traits>
 
+#include "pbllm_stream.cuh"
 #include "pbllm_tc_ptx.cuh"
 
 namespace pbl {
@@ -31,15 +34,15 @@ namespace pbl {
 namespace dk {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
-constexpr int kTok = 8;                       // tokens per pass (mma N)
-constexpr int kTileBytes = kRgRows * kTileCols * 2;   // 4096: the warp's 32x64 16-bit weight tile (128B rows, swizzled)
+constexpr int kTok = 8;                       // tokens per group (mma N)
+constexpr int kTileBytes = kRgRows * kTileCols * 2;   // 4096: the warp's 32x64 16-bit tile (128B rows, swizzled)
 constexpr int kHeadBytes = kRgRows * kTok * 4;        // 1024 per token group: the warp's head-segment partial (fp32 [tokens][32 rows])
 constexpr int kWarpBytes = kTileBytes + kHeadBytes;   // 5120 (one token group per pass); two groups: + kHeadBytes
-constexpr int kOut = kRgRows * kTok;          // 256 outputs per (row group, token pass) == kThreads
+constexpr int kOut = kRgRows * kTok;          // 256 outputs per (row group, token group) == kThreads
 static_assert(kOut == kThreads, "one thread per output in the cross-warp reduction");
 
 struct Params {
-    const uint2* dsign;
+    const uint2* fsign;
     const uint32_t* eptr;
     const uint4* ent;
     const float2* affine;
@@ -54,6 +57,7 @@ struct Params {
     uint32_t rgs;
     uint32_t slots;       // partial slots per row group
     uint32_t q, rem;      // blocks per warp: nblocks / (grid * 8) and the remainder (the first `rem` warps take one more)
+    uint32_t has_mid;     // some (row, group) has lo != -hi: the mid * sum(x) term is needed
     unsigned long long* trace;   // kTrace builds only: [cta][warp][8] globaltimer stamps of this launch
 };
 }  // namespace dk
@@ -79,57 +83,46 @@ __device__ __forceinline__ void dk_ldsm4(uint32_t addr, uint32_t& r0, uint32_t& 
                  : "memory");
 }
 
-// Tile layout.  The warp's 32x64 tile has 128-byte rows of eight 16-byte chunks, chunk pc stored at
-// row*128 + ((pc ^ (row & 7)) << 4) (conflict-free for the row-per-lane stores and for ldmatrix).  Columns are PERMUTED
-// inside a row so that the activations never go through shared memory: chunk pc, 32-bit word t holds the logical
-// columns 16t + 2pc + {0,1}.  ldmatrix then hands lane (g, t) of k16-step q exactly the columns 16t + 4q + {0,1} (a0/a1)
-// and 16t + 4q + {2,3} (a2/a3) -- the columns of words 2q and 2q+1 of the 16 consecutive activations that lane loaded
-// from global memory (token g, columns 16t..16t+15), which therefore ARE its B fragments.
-//
-// 64 sign bits of one weight row -> 64 exact {lo,hi} 16-bit values, 8 STS.128: PRMT byte-sign replicate + LOP3 select
-// as in expand_row; `brow` already carries (row & 7) << 4, so chunk pc is at brow ^ (pc << 4).
-__device__ __forceinline__ void dk_expand_dense(const uint2 sg, const uint32_t LL, const uint32_t DD, const uint32_t brow) {
-#pragma unroll
-    for (int jq = 0; jq < 4; ++jq) {                    // bit 2pc (+16 for odd t) of a sign word = byte pc>>2 (+2), bit 2*(pc&3)
-        const int j = 2 * jq;
-        const uint32_t xa0 = sg.x << (7 - j), xb0 = sg.x << (6 - j), xa1 = sg.y << (7 - j), xb1 = sg.y << (6 - j);
-#pragma unroll
-        for (int by0 = 0; by0 < 2; ++by0) {
-            const int pc = jq + 4 * by0;
-            uint32_t h[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const uint32_t by = (uint32_t)(by0 + 2 * (t & 1));
-                const uint32_t sel = 0x8888u | by | (by << 4) | ((4u + by) << 8) | ((4u + by) << 12);
-                h[t] = sel_xor_and(LL, DD, (t >> 1) ? prmt(xa1, xb1, sel) : prmt(xa0, xb0, sel));
-            }
-            sts_v4(brow ^ ((uint32_t)pc << 4), h[0], h[1], h[2], h[3]);
-        }
-    }
-}
+// Tile layout (st::tile_slot).  The warp's 32x64 tile has 128-byte rows of eight 16-byte chunks, chunk pc
+// stored at row*128 + ((pc ^ (row & 7)) << 4) (conflict-free for ldmatrix).  Columns are PERMUTED inside a row so that the
+// activations never go through shared memory: chunk pc, 32-bit word t holds the logical columns 16t + 2pc + {0,1}.
+// ldmatrix then hands lane (g, t) of k16-step q exactly the columns 16t + 4q + {0,1} (a0/a1) and 16t + 4q + {2,3} (a2/a3)
+// -- the columns of words 2q and 2q+1 of the 16 consecutive activations that lane loaded from global memory (token g,
+// columns 16t..16t+15), which therefore ARE its B fragments.  The dense A fragments built from the sign words use the same
+// column assignment (st::sign_pos).
 
-// four salient entries: store each value's 16 bits at its (pre-swizzled) byte offset in the tile
+// {+1,+1} in the layer's 16-bit type: the rest state of every tile word
+template <typename T> __device__ __forceinline__ constexpr uint32_t dk_one2() { return std::is_same<T, __half>::value ? 0x3C003C00u : 0x3F803F80u; }
+
+// four salient entries: store each tau at its slot of the tile (entry >> 20 = 2 * slot) / reset the slots to +1.0
 __device__ __forceinline__ void dk_patch4(const uint32_t tile_s, const uint4 e) {
-    sts_u16(tile_s + (e.x >> 16), (uint16_t)e.x);
-    sts_u16(tile_s + (e.y >> 16), (uint16_t)e.y);
-    sts_u16(tile_s + (e.z >> 16), (uint16_t)e.z);
-    sts_u16(tile_s + (e.w >> 16), (uint16_t)e.w);
+    sts_u16(tile_s + (e.x >> 20), (uint16_t)e.x);
+    sts_u16(tile_s + (e.y >> 20), (uint16_t)e.y);
+    sts_u16(tile_s + (e.z >> 20), (uint16_t)e.z);
+    sts_u16(tile_s + (e.w >> 20), (uint16_t)e.w);
+}
+__device__ __forceinline__ void dk_unpatch4(const uint32_t tile_s, const uint4 e, const uint16_t one) {
+    sts_u16(tile_s + (e.x >> 20), one);
+    sts_u16(tile_s + (e.y >> 20), one);
+    sts_u16(tile_s + (e.z >> 20), one);
+    sts_u16(tile_s + (e.w >> 20), one);
 }
 
-// kOcc = CTAs per SM the register budget is sized for: 3 -> 85 registers, 4 -> 64
 __device__ __forceinline__ unsigned long long dk_now() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
 
-// kNT = token groups of 8 per pass: 1 (M <= 8), or 2 (9..16 tokens against ONE expansion of each tile; the second group
-// lives in its own variables, so the one-group instance compiles to exactly the code it had before)
-template <typename T, int kOcc, bool kTrace = false, int kNT = 1>
+// kNT = token groups of 8 per pass: 1 (M <= 8), or 2 (9..16 tokens against ONE expansion of each block; the second group
+// lives in its own variables).  kLean = the common case compiled without its branches: one group per row, activations
+// 32-byte aligned with K a multiple of 64 (the launcher checks).
+template <typename T, int kOcc, bool kTrace = false, int kNT = 1, bool kLean = false>
 __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk::Params p) {
     using namespace dk;
     constexpr int kWarpBytes = dk::kWarpBytes + (kNT - 1) * kHeadBytes;
     constexpr int kTokP = kTok * kNT, kOutP = kOut * kNT;
+    constexpr uint32_t kOne2 = dk_one2<T>();
     unsigned long long tr[8];
     if (kTrace) { tr[0] = dk_now(); }
     extern __shared__ __align__(128) uint8_t smem[];
@@ -141,6 +134,10 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     const uint32_t tile_s = smem_u32(wsm);
     float* head_red = reinterpret_cast<float*>(wsm + kTileBytes);
     float* tail_red = reinterpret_cast<float*>(wsm);      // aliases the tile: written only after the warp's last block
+
+    // the tile starts (and, after every block, is again) +1.0 everywhere
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sts_v4(tile_s + lane * 16u + (uint32_t)i * 512u, kOne2, kOne2, kOne2, kOne2);
 
     // ---- work partition (division-free): warp gw owns blocks [gw*q + min(gw,rem), ...), q = B / warps, rem = B % warps ----
     const uint32_t TC = p.tiles_c, q = p.q, rem = p.rem;
@@ -155,7 +152,7 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // first loads of this warp's stream: sign words and entry offsets of its run (eptr lives in registers, one per lane)
-    const uint2* sgp = p.dsign + (size_t)w_lo * kRgRows + lane;
+    const uint2* sgp = p.fsign + (size_t)w_lo * kRgRows + lane;
     uint2 sg = make_uint2(0, 0);
     uint32_t epr = 0;
     if (w_lo < w_hi) {
@@ -165,10 +162,20 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     uint32_t rg = 0, kb = 0;
     if (w_lo < w_hi) { rg = w_lo / TC; kb = w_lo - rg * TC; }
     const uint32_t rg_first = rg;
-    const bool grouped = p.groups > 1;
+    const bool grouped = !kLean && p.groups > 1;
+    const bool has_mid = p.has_mid != 0u;
     uint32_t cur_g = grouped ? kb / p.tiles_per_group : 0u;
-    float2 af = make_float2(0.f, 0.f);
-    if (w_lo < w_hi) af = __ldg(p.affine + (size_t)(rg * kRgRows + lane) * p.groups + cur_g);
+    const uint32_t g4 = lane >> 2, t4 = lane & 3u;
+    // the {lo, hi} of this lane's four accumulator rows g4 + 8j of the current (row group, group): loaded when the segment
+    // starts, first used when it ends (fold)
+    float2 lv[4];
+    auto load_levels = [&](uint32_t rgi, uint32_t grp) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) lv[j] = __ldg(p.affine + (size_t)(rgi * kRgRows + g4 + 8u * j) * p.groups + grp);
+    };
+#pragma unroll
+    for (int j = 0; j < 4; ++j) lv[j] = make_float2(0.f, 0.f);
+    if (w_lo < w_hi) load_levels(rg, cur_g);
 
     if (lane == 0) { s_hrg[wid] = kNone; s_trg[wid] = kNone; }
     if (tid == 0) {                               // which of this CTA's row groups are shared with other CTAs, and how
@@ -188,7 +195,7 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
 
     uint32_t ci = 0;                               // index of the current block in the eptr register chunk
     // the first min(n4, 64) units of a block sit in two register sets of h1 = ceil/2 and the rest: unit `lane` and unit
-    // `h1 + lane` (the index builder deals entries to units so that each of the 8 patch stores is bank-conflict free)
+    // `h1 + lane` (the packer deals entries to units so that each of the 8 patch stores is bank-conflict free)
     struct Ent { uint4 a, c; uint32_t eb, n4; };        // one block's entries: units `lane` and `h1 + lane`, offset, unit count
     auto ent_load = [&](Ent& E, uint32_t i) {           // i = index of the block in this warp's eptr register chunk
         E.eb = __shfl_sync(0xffffffffu, epr, i);
@@ -200,27 +207,22 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
         if (lane + h1 < n1) E.c = __ldg(e + h1);
     };
     Ent E0, E1;                                         // two blocks of entries in flight: each set is reloaded for the block
-    E0.a = E0.c = E1.a = E1.c = make_uint4(0, 0, 0, 0); // after next right after its patch -- two blocks of cover
+    E0.a = E0.c = E1.a = E1.c = make_uint4(0, 0, 0, 0); // after next right after its un-patch -- two blocks of cover
     E0.eb = E0.n4 = E1.eb = E1.n4 = 0;
     if (w_lo < w_hi) ent_load(E0, 0);
     if (w_lo + 1u < w_hi) ent_load(E1, 1);
-    uint32_t LL, DD;
-    {
-        const uint32_t lo = bits16<T>(af.x), hi = bits16<T>(af.y);
-        LL = lo | (lo << 16);
-        DD = (lo ^ hi) * 0x10001u;
-    }
 
     // ---- activation loads: lane -> (token = lane>>2, 16-column segment = lane&3) of the 8 x 64 block ----------
     const uint32_t xtok = lane >> 2, xseg = lane & 3u;
-    const bool x_fast = ((p.ldx & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15u) == 0) && ((p.K & 63) == 0);
-    const bool x_fast256 = x_fast && ((p.ldx & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 31u) == 0);   // one 32 B load
+    const bool x_fast = kLean || (((p.ldx & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15u) == 0) && ((p.K & 63) == 0));
+    const bool x_fast256 = kLean || (x_fast && ((p.ldx & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 31u) == 0));   // one 32 B load
     const bool x_tok_ok = (m0 + (int)xtok) < p.M;
     // byte offset of (my token row, my 16-column segment, k-block 0); 32-bit (checked by the launcher) and opaque to the
     // compiler so it stays in a register instead of being recomputed every block
     uint32_t xoff_row = (uint32_t)(((int64_t)(m0 + (x_tok_ok ? (int)xtok : 0)) * p.ldx + 16 * xseg) * 2);
     asm volatile("" : "+r"(xoff_row));
-    uint32_t xoff = xoff_row + kb * (kTileCols * 2u);          // loop-carried: advances one k-block per iteration
+    uint32_t xoff = xoff_row + kb * (kTileCols * 2u);          // loop-carried: offset of the NEXT block to load
+    uint32_t xkb = kb;                                         // and its k-block
     const bool x_tok_ok2 = kNT == 2 && (m0 + kTok + (int)xtok) < p.M;                      // second token group
     uint32_t xoff_row2 = (uint32_t)(((int64_t)(x_tok_ok2 ? m0 + kTok + (int)xtok : m0) * p.ldx + 16 * xseg) * 2);
     if constexpr (kNT == 2) asm volatile("" : "+r"(xoff_row2));
@@ -253,26 +255,60 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
             xb = make_uint4(w[4], w[5], w[6], w[7]);
         }
     };
-    auto load_x = [&](uint32_t kblk, uint4& xa, uint4& xb) { load_x_at(kblk, xoff, x_tok_ok, xa, xb); };
+    struct XF { uint4 a, b, a2, b2; };                   // the B fragments of one block (second token group: a2, b2)
+    auto load_x_next = [&](XF& X) {                      // load the next block in line, then advance the line
+        load_x_at(xkb, xoff, x_tok_ok, X.a, X.b);
+        if constexpr (kNT == 2) load_x_at(xkb, xoff2, x_tok_ok2, X.a2, X.b2);
+        ++xkb;
+        const bool wrap = xkb == TC;
+        xkb = wrap ? 0u : xkb;
+        xoff = wrap ? xoff_row : xoff + kTileCols * 2u;
+        if constexpr (kNT == 2) xoff2 = wrap ? xoff_row2 : xoff2 + kTileCols * 2u;
+    };
 
-    // shared-memory addresses of this lane
-    const uint32_t r7 = lane & 7u;
-    const uint32_t brow = (tile_s + lane * 128u) | (r7 << 4);                     // my weight row; chunk c lives at brow ^ (c << 4)
-    const uint32_t lm_row = (lane & 7u) + ((lane >> 3) & 1u) * 8u;                // A fragments (weights)
+    // ldmatrix row addresses of this lane (A fragments of the correction tile), one per k16 step
+    const uint32_t lm_row = (lane & 7u) + ((lane >> 3) & 1u) * 8u;
     const uint32_t lm_base0 = tile_s + lm_row * 128u + (((lane >> 4) ^ (lm_row & 7u)) << 4);
-    const uint32_t g4 = lane >> 2, t4 = lane & 3u;
-    uint32_t lm_q[4];                                                             // ldmatrix row address per k16 step
+    uint32_t lm_q[4];
 #pragma unroll
     for (int qi = 0; qi < 4; ++qi) {
         lm_q[qi] = lm_base0 ^ ((uint32_t)qi << 5);
         asm volatile("" : "+r"(lm_q[qi]));                                        // keep in a register (no rematerialisation)
     }
-    uint32_t brow_r = brow;
-    asm volatile("" : "+r"(brow_r));
 
-    float acc[2][4], acc2[2][4];                  // acc2: second token group (kNT == 2)
+    // accumulators, all in the mma C layout (h = rows 0-15 / 16-31; i: row g4 + 8*(i>>1), token 2*t4 + (i&1)):
+    //   acc_d  sum of t_ij x (+-1 plane and tau) of the current (row group, group) segment
+    //   acc_x  sum of x over the segment's columns (identical in every row)
+    //   acc    the folded result: mid * acc_x + half * acc_d of the finished segments
+    float acc[2][4], acc_d[2][4], acc_x[4];
+    float acc2[2][4], acc_d2[2][4], acc_x2[4];     // second token group (kNT == 2)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[0][i] = acc[1][i] = acc2[0][i] = acc2[1][i] = 0.f;
+    for (int i = 0; i < 4; ++i) {
+        acc[0][i] = acc[1][i] = acc_d[0][i] = acc_d[1][i] = acc_x[i] = 0.f;
+        acc2[0][i] = acc2[1][i] = acc_d2[0][i] = acc_d2[1][i] = acc_x2[i] = 0.f;
+    }
+    auto fold = [&]() {                             // apply the levels of the finished (row group, group) segment
+        float mid[4], half[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { mid[j] = 0.5f * (lv[j].x + lv[j].y); half[j] = 0.5f * (lv[j].y - lv[j].x); }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = 2 * h + (i >> 1);
+                acc[h][i] = fmaf(half[j], acc_d[h][i], acc[h][i]);
+                if (has_mid) acc[h][i] = fmaf(mid[j], acc_x[i & 1], acc[h][i]);
+                acc_d[h][i] = 0.f;
+                if constexpr (kNT == 2) {
+                    acc2[h][i] = fmaf(half[j], acc_d2[h][i], acc2[h][i]);
+                    if (has_mid) acc2[h][i] = fmaf(mid[j], acc_x2[i & 1], acc2[h][i]);
+                    acc_d2[h][i] = 0.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc_x[i] = acc_x2[i] = 0.f;
+    };
 
     // fp32 [token][row] layout of one row group's outputs: index m*32 + r
     auto store_frag = [&](float* dst) {
@@ -296,37 +332,63 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     if (kTrace) tr[1] = dk_now();
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (kTrace) tr[2] = dk_now();
-    uint4 xa = make_uint4(0, 0, 0, 0), xb = make_uint4(0, 0, 0, 0);
-    uint4 xa2 = make_uint4(0, 0, 0, 0), xb2 = make_uint4(0, 0, 0, 0);
-    if (w_lo < w_hi) load_x(kb, xa, xb);
-    if constexpr (kNT == 2) { if (w_lo < w_hi) load_x_at(kb, xoff2, x_tok_ok2, xa2, xb2); }
+    XF X0, X1;
+    X0.a = X0.b = X0.a2 = X0.b2 = X1.a = X1.b = X1.a2 = X1.b2 = make_uint4(0, 0, 0, 0);
+    if (w_lo < w_hi) load_x_next(X0);
+    __syncwarp();                                       // the initialised tile is visible to the whole warp
 
-    // Every stream is prefetched IN PLACE: a register set is reloaded right after its last use (sign words, activations:
-    // one block of cover; salient entries, the stream that comes from DRAM with a dependent address: two sets, two blocks).
-    auto do_block = [&](const uint32_t blk, Ent& E) {
+    // Every stream is prefetched into registers: sign words one block ahead (reloaded in place), activations one block
+    // ahead (two register sets), salient entries -- the stream that comes from DRAM with a dependent address -- two blocks
+    // ahead (two sets; each is reloaded right after its un-patch).
+    const uint16_t one16 = (uint16_t)kOne2;
+    auto do_block = [&](const uint32_t blk, Ent& E, const XF& X, XF& Xn) {
         const bool more = blk + 1 < w_hi;
         if (grouped) {
             const uint32_t g = kb / p.tiles_per_group;
-            if (g != cur_g) {
+            if (g != cur_g) {                           // a new group of this row group: fold the finished one, fetch the new levels
+                fold();
                 cur_g = g;
-                af = __ldg(p.affine + (size_t)(rg * kRgRows + lane) * p.groups + g);
-                const uint32_t lo = bits16<T>(af.x), hi = bits16<T>(af.y);
-                LL = lo | (lo << 16);
-                DD = (lo ^ hi) * 0x10001u;
+                load_levels(rg, g);
             }
         }
+        if (more) load_x_next(Xn);                      // the next block's activations: a whole block of cover
 
-        __syncwarp();                                   // the previous block's ldmatrix reads are done
-        dk_expand_dense(sg, LL, DD, brow_r);
+        // salient entries into the tile
+        const uint32_t n1 = min(E.n4, 64u), h1 = (n1 + 1u) >> 1;
+        if (lane < h1) dk_patch4(tile_s, E.a);
+        if (lane + h1 < n1) dk_patch4(tile_s, E.c);
+        for (uint32_t i = 64u + lane; i < E.n4; i += 32u) dk_patch4(tile_s, __ldg(p.ent + (E.eb + i)));   // rare: > 256 salient in a block
+        __syncwarp();                                   // the patched tile is complete and visible to the whole warp
+
+        // the block on the tensor cores: A fragments = tile words with the sign bits XORed in, B fragments = the activation registers
+        const uint32_t xw[8] = {X.a.x, X.a.y, X.a.z, X.a.w, X.b.x, X.b.y, X.b.z, X.b.w};
+        const uint32_t xw2[8] = {X.a2.x, X.a2.y, X.a2.z, X.a2.w, X.b2.x, X.b2.y, X.b2.z, X.b2.w};
+#pragma unroll
+        for (int qi = 0; qi < 4; ++qi) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t wd = h ? sg.y : sg.x;
+                uint32_t t0, t1, t2, t3;
+                dk_ldsm4(lm_q[qi] + (uint32_t)h * 2048u, t0, t1, t2, t3);
+                const uint32_t a0 = ((wd << (4 * qi + 0)) & 0x80008000u) ^ t0;
+                const uint32_t a1 = ((wd << (4 * qi + 1)) & 0x80008000u) ^ t1;
+                const uint32_t a2 = ((wd << (4 * qi + 2)) & 0x80008000u) ^ t2;
+                const uint32_t a3 = ((wd << (4 * qi + 3)) & 0x80008000u) ^ t3;
+                dk_mma<T>(acc_d[h], a0, a1, a2, a3, xw[2 * qi], xw[2 * qi + 1]);
+                if constexpr (kNT == 2) dk_mma<T>(acc_d2[h], a0, a1, a2, a3, xw2[2 * qi], xw2[2 * qi + 1]);
+            }
+            if (has_mid) {                              // sum of x over the block's columns: all-ones A fragment
+                dk_mma<T>(acc_x, kOne2, kOne2, kOne2, kOne2, xw[2 * qi], xw[2 * qi + 1]);
+                if constexpr (kNT == 2) dk_mma<T>(acc_x2, kOne2, kOne2, kOne2, kOne2, xw2[2 * qi], xw2[2 * qi + 1]);
+            }
+        }
         sgp += more ? kRgRows : 0;                      // unconditional reload (the last block re-reads itself): the load
         sg = __ldg(sgp);                                // must land in `sg` directly, not in a temporary that is moved at once
-        __syncwarp();                                   // dense rows land before other lanes patch them
-        {
-            const uint32_t n1 = min(E.n4, 64u), h1 = (n1 + 1u) >> 1;
-            if (lane < h1) dk_patch4(tile_s, E.a);
-            if (lane + h1 < n1) dk_patch4(tile_s, E.c);
-            for (uint32_t i = 64u + lane; i < E.n4; i += 32u) dk_patch4(tile_s, __ldg(p.ent + (E.eb + i)));   // rare: > 256 salient in a block
-        }
+
+        __syncwarp();                                   // every lane's ldmatrix reads are done: reset the entries to +1.0
+        if (lane < h1) dk_unpatch4(tile_s, E.a, one16);
+        if (lane + h1 < n1) dk_unpatch4(tile_s, E.c, one16);
+        for (uint32_t i = 64u + lane; i < E.n4; i += 32u) dk_unpatch4(tile_s, __ldg(p.ent + (E.eb + i)), one16);
         ++ci;
         if (blk + 2u < w_hi) {                          // this set's next block is the one after next
             if (ci + 2u > 31u) {                        // rare: refill the eptr registers (runs longer than 30 blocks)
@@ -335,38 +397,17 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
             }
             ent_load(E, ci + 1u);
         }
-        __syncwarp();                                   // the tile is complete and visible to the whole warp
+        __syncwarp();                                   // the resets land before the next block's patch stores (other lanes, same slots)
 
-        // tensor cores: A fragments by ldmatrix from the tile, B fragments straight from the activation registers
-        {
-            const uint32_t xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-            const uint32_t xw2[8] = {xa2.x, xa2.y, xa2.z, xa2.w, xb2.x, xb2.y, xb2.z, xb2.w};
-#pragma unroll
-            for (int qi = 0; qi < 4; ++qi) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t a0, a1, a2, a3;
-                    dk_ldsm4(lm_q[qi] + (uint32_t)h * 2048u, a0, a1, a2, a3);
-                    dk_mma<T>(acc[h], a0, a1, a2, a3, xw[2 * qi], xw[2 * qi + 1]);
-                    if constexpr (kNT == 2) dk_mma<T>(acc2[h], a0, a1, a2, a3, xw2[2 * qi], xw2[2 * qi + 1]);
-                }
-            }
-        }
         ++kb;
         const bool rg_end = kb == TC;
-        xoff = rg_end ? xoff_row : xoff + kTileCols * 2u;
-        load_x(rg_end ? 0u : kb, xa, xb);               // unconditional: the address after the last block is still inside x
-        if constexpr (kNT == 2) {
-            xoff2 = rg_end ? xoff_row2 : xoff2 + kTileCols * 2u;
-            load_x_at(rg_end ? 0u : kb, xoff2, x_tok_ok2, xa2, xb2);
-        }
 
         // ---- end of this warp's part of the row group? -----------------------------------------------------
         if (rg_end || !more) {
+            fold();
             const bool whole = rg_end && (w_lo <= rg * TC);      // this warp saw every k-block of the row group
             if (whole) {                                         // finish it here: + bias, round, store
-                __syncwarp();
-                store_frag(tail_red);
+                store_frag(tail_red);                            // (the tile is at rest and not read again before the next patch)
                 __syncwarp();
                 const int orow = (int)(rg * kRgRows + lane);
                 if (orow < p.N) {
@@ -376,11 +417,16 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
                         if (m0 + m < p.M)
                             reinterpret_cast<T*>(p.y)[(int64_t)(m0 + m) * p.ldy + orow] = from_f32<T>(bv + tail_red[m * kRgRows + lane]);
                 }
+                __syncwarp();
+                if (more) {                                      // the staging area is the tile: back to +1.0
+#pragma unroll
+                    for (int i = 0; i < kNT * 2; ++i) sts_v4(tile_s + lane * 16u + (uint32_t)i * 512u, kOne2, kOne2, kOne2, kOne2);
+                    __syncwarp();
+                }
             } else if (rg == rg_first) {
                 store_frag(head_red);                            // head partial: its own buffer, the warp may go on
                 if (lane == 0) s_hrg[wid] = rg;
             } else {
-                __syncwarp();
                 store_frag(tail_red);                            // tail partial: last thing this warp does
                 if (lane == 0) s_trg[wid] = rg;
             }
@@ -391,17 +437,14 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
                 ++rg;
                 if (more) {
                     cur_g = 0;
-                    af = __ldg(p.affine + (size_t)(rg * kRgRows + lane) * p.groups);
-                    const uint32_t lo = bits16<T>(af.x), hi = bits16<T>(af.y);
-                    LL = lo | (lo << 16);
-                    DD = (lo ^ hi) * 0x10001u;
+                    load_levels(rg, 0u);
                 }
             }
         }
     };
-    for (uint32_t blk = w_lo; blk < w_hi; blk += 2u) {   // unrolled by two: the entry sets alternate without register moves
-        do_block(blk, E0);
-        if (blk + 1u < w_hi) do_block(blk + 1u, E1);
+    for (uint32_t blk = w_lo; blk < w_hi; blk += 2u) {   // unrolled by two: the register sets alternate without moves
+        do_block(blk, E0, X0, X1);
+        if (blk + 1u < w_hi) do_block(blk + 1u, E1, X1, X0);
     }
 
     // ---- cross-warp reduction in shared memory; row groups shared with other CTAs go through the workspace ----------
@@ -505,114 +548,13 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     trace_out();
 }
 
-// ---- decode index construction (one-time, from the packed form) ---------------------------------------------------
-// pass 1: 16-byte units of salient entries per block, row-group-major order; scanned in place afterwards
-__global__ void decode_index_count_kernel(const uint32_t* __restrict__ vptr, uint32_t* __restrict__ eptr, uint32_t tiles_c,
-                                          uint32_t nblocks) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nblocks) return;
-    const uint32_t rg = i / tiles_c, kb = i - rg * tiles_c;
-    const uint32_t tr = rg / kRgPerTile, rgi = rg % kRgPerTile;
-    const size_t old = ((size_t)tr * tiles_c + kb) * kRgPerTile + rgi;
-    const uint32_t cnt = vptr[old + 1] - vptr[old];
-    eptr[i] = (cnt + 3u) / 4u;
-}
-
-// pass 2: sign words and entries. CTA = one 128x64 plane tile, warp = one 32-row group, lane = row.
-// Entry order inside a block is chosen for the kernel's patch stores: store j of register set a writes the entries at
-// slots 4*(a*h1 + lane) + j, lane = 0..31 -- a "group" of up to 32 entries that should fall in 32 different shared-memory
-// banks.  Entries are ranked by (bank, row, column) and rank k goes to group k % 8, position k / 8: the <= 8 entries of
-// one bank land in 8 different groups.  (A row touches each bank at most twice, so per-bank counts come from two
-// ballots.)  Blocks with more than 256 entries keep ranks >= 256 in rank order behind the first 64 units.
-__global__ void __launch_bounds__(128) decode_index_fill_kernel(const uint4* __restrict__ planes, const uint32_t* __restrict__ vptr,
-                                                                const uint16_t* __restrict__ vals, const uint32_t* __restrict__ eptr,
-                                                                uint32_t tiles_c, uint2* __restrict__ dsign,
-                                                                uint32_t* __restrict__ ent) {
-    const uint32_t lane = threadIdx.x & 31u, rgi = threadIdx.x >> 5;
-    const size_t tile = blockIdx.x;
-    const uint32_t tr = (uint32_t)(tile / tiles_c), kb = (uint32_t)(tile % tiles_c);
-    const uint4 pw = planes[tile * kTileRows + rgi * kRgRows + lane];
-    const size_t blk = (size_t)(tr * kRgPerTile + rgi) * tiles_c + kb;
-    dsign[blk * kRgRows + lane] = make_uint2(pw.x, pw.y);
-    const size_t old = tile * kRgPerTile + rgi;
-    const uint32_t vbase = vptr[old], cnt = vptr[old + 1] - vbase;
-    if (cnt == 0) return;                                   // warp-uniform
-    const uint32_t mine = (uint32_t)(__popc(pw.z) + __popc(pw.w));
-    const uint32_t voff = warp_excl_scan(mine, lane);       // my row's first value in the packed (row, column) order
-    uint32_t* dst = ent + (size_t)eptr[blk] * 4u;
-    const uint32_t n4 = (cnt + 3u) / 4u, n1 = min(n4, 64u), h1 = (n1 + 1u) >> 1;
-
-    // my row's entries and the banks they hit (each bank at most twice per row: two columns per 32-bit word)
-    uint32_t my_e[64];
-    uint32_t m1 = 0, m2 = 0, ne = 0;
-#pragma unroll 1
-    for (int wd = 0; wd < 2; ++wd) {
-        uint32_t m = wd ? pw.w : pw.z;
-        while (m) {
-            const uint32_t col = (uint32_t)(__ffs(m) - 1) + 32u * wd;
-            m &= m - 1u;
-            const uint32_t pc = (col >> 1) & 7u;                                             // chunk, word, half: see "Tile layout"
-            const uint32_t pos = lane * 128u + ((pc ^ (lane & 7u)) << 4) + (col >> 4) * 4u + (col & 1u) * 2u;
-            my_e[ne] = (pos << 16) | (uint32_t)vals[vbase + voff + ne];
-            ++ne;
-            const uint32_t bit = 1u << ((pos >> 2) & 31u);
-            m2 |= m1 & bit;
-            m1 |= bit;
-        }
-    }
-    // rank of my first entry in every bank: entries of lower banks + entries of this bank in lower rows
-    uint16_t start[32];
-    uint32_t base = 0;
-    const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll 1
-    for (int bnk = 0; bnk < 32; ++bnk) {
-        const uint32_t b1 = __ballot_sync(0xffffffffu, (m1 >> bnk) & 1u), b2 = __ballot_sync(0xffffffffu, (m2 >> bnk) & 1u);
-        start[bnk] = (uint16_t)(base + __popc(b1 & lt) + __popc(b2 & lt));
-        base += __popc(b1) + __popc(b2);
-    }
-    // every slot first gets a copy of one real entry (padding must be an idempotent store), then the real entries land
-    const uint32_t first_lane = (uint32_t)__ffs(__ballot_sync(0xffffffffu, ne > 0)) - 1u;
-    const uint32_t pad = __shfl_sync(0xffffffffu, ne ? my_e[0] : 0u, first_lane);
-    for (uint32_t sl = lane; sl < n4 * 4u; sl += 32u) dst[sl] = pad;
-    __syncwarp();
-#pragma unroll 1
-    for (uint32_t i = 0; i < ne; ++i) {
-        const uint32_t e = my_e[i];
-        const uint32_t k = start[(e >> 18) & 31u]++;
-        uint32_t slot = k;
-        if (k < 256u) {
-            const uint32_t g = k & 7u, idx = k >> 3;
-            slot = 4u * ((g >> 2) * h1 + idx) + (g & 3u);
-        }
-        dst[slot] = e;
-    }
-}
-
-void launch_scan_counts(uint32_t* v, int64_t n, cudaStream_t s);   // pbllm_pack.cu
-
-int launch_decode_index_count(const Layer& L, uint32_t* eptr, cudaStream_t s) {
-    const uint32_t nblocks = (uint32_t)(L.tiles_r * kRgPerTile * L.tiles_c);
-    decode_index_count_kernel<<<(nblocks + 255u) / 256u, 256, 0, s>>>(L.vptr, eptr, (uint32_t)L.tiles_c, nblocks);
-    int rc = check_cuda(cudaGetLastError(), "decode_index_count launch");
-    if (rc) return rc;
-    launch_scan_counts(eptr, nblocks, s);
-    count_launch(2);
-    return check_cuda(cudaGetLastError(), "decode_index scan launch");
-}
-
-int launch_decode_index_fill(const Layer& L, const uint32_t* eptr, uint2* dsign, uint32_t* ent, cudaStream_t s) {
-    decode_index_fill_kernel<<<(unsigned)(L.tiles_r * L.tiles_c), 128, 0, s>>>(L.planes, L.vptr, (const uint16_t*)L.vals, eptr,
-                                                                               (uint32_t)L.tiles_c, dsign, ent);
-    count_launch();
-    return check_cuda(cudaGetLastError(), "decode_index_fill launch");
-}
-
 // ---- host side -------------------------------------------------------------------------------------------------
+static int dk_occupancy();
 static int dk_ctas_per_sm() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("PBL_DK_CTAS");
-        v = (e && *e) ? atoi(e) : 3;                  // measured on B200: 3 CTAs (24 warps) per SM is the fastest grid
+        v = (e && *e) ? atoi(e) : dk_occupancy();     // grid = SMs x resident CTAs per SM
         if (v < 1) v = 1;
         if (v > 16) v = 16;
     }
@@ -623,8 +565,8 @@ static int dk_occupancy() {      // which register budget / launch-bounds varian
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("PBL_DK_OCC");
-        v = (e && *e) ? atoi(e) : 3;
-        if (v != 4) v = 3;
+        v = (e && *e) ? atoi(e) : 2;                  // 2 -> up to 128 registers (no spills), 3 -> 80 registers
+        if (v != 3) v = 2;
     }
     return v;
 }
@@ -684,9 +626,9 @@ static DecodeGeom decode_geom_raw(int64_t tiles_r, int64_t tiles_c, int64_t M, u
 }
 
 bool decode_supported(const Layer& L, int64_t ldx, int64_t M) {
-    if (!L.dsign || !L.eptr || !L.ent) return false;
+    if (!L.fsign || !L.eptr || !L.ent) return false;
     if (L.dtype != PBL_F16 && L.dtype != PBL_BF16) return false;
-    if (M <= 0 || M > 64) return false;
+    if (M <= 0 || M > 65535LL * 16) return false;                                      // grid.y = token passes
     if (ldx <= 0 || (uint64_t)M * (uint64_t)ldx * 2u >= (1ull << 31)) return false;   // 32-bit activation offsets
     return true;
 }
@@ -696,7 +638,7 @@ size_t decode_workspace_bytes(const Layer& L, int64_t M) {
     return decode_geom(L, M).ws_bytes;
 }
 
-template <typename T, int kOcc, int kNT>
+template <typename T, int kOcc, int kNT, bool kLean>
 static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws, cudaStream_t s) {
     const DecodeGeom g = decode_geom(L, M);
     const int smem = dk::kWarps * (dk::kWarpBytes + (kNT - 1) * dk::kHeadBytes);
@@ -705,13 +647,14 @@ static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, 
     cudaGetDevice(&cur_dev);
     if (cur_dev < 0 || cur_dev >= 64) cur_dev = 0;
     if (attr_smem_dev[cur_dev] < smem) {
-        int rc = check_cuda(cudaFuncSetAttribute(decode_mma_kernel<T, kOcc, false, kNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+        int rc = check_cuda(cudaFuncSetAttribute(decode_mma_kernel<T, kOcc, false, kNT, kLean>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                             "cudaFuncSetAttribute(decode smem)");
         if (rc) return rc;
         attr_smem_dev[cur_dev] = smem;
     }
     dk::Params p;
-    p.dsign = L.dsign; p.eptr = L.eptr; p.ent = reinterpret_cast<const uint4*>(L.ent);
+    p.fsign = L.fsign; p.eptr = L.eptr; p.ent = reinterpret_cast<const uint4*>(L.ent);
+    p.has_mid = (L.flags & PBL_LAYER_HAS_MID) ? 1u : 0u;
     p.affine = L.affine; p.bias = L.bias; p.x = x; p.y = y; p.ldx = ldx; p.ldy = ldy;
     p.ws_part = ws;
     p.M = (int)M; p.N = (int)L.N; p.K = (int)L.K;
@@ -731,14 +674,14 @@ static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, 
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     cudaError_t le;
-    if (g_trace && g_trace_next < g_trace_launches && kOcc == 3 && kNT == 1) {
+    if (g_trace && g_trace_next < g_trace_launches && kOcc == 2 && kNT == 1 && !kLean) {
         p.trace = g_trace + (g_trace_next++) * kTraceStride;
         static bool tattr = false;
-        if (!tattr) { cudaFuncSetAttribute(decode_mma_kernel<T, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); tattr = true; }
-        le = cudaLaunchKernelEx(&cfg, decode_mma_kernel<T, 3, true>, p);
+        if (!tattr) { cudaFuncSetAttribute(decode_mma_kernel<T, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); tattr = true; }
+        le = cudaLaunchKernelEx(&cfg, decode_mma_kernel<T, 2, true>, p);
     } else {
         p.trace = nullptr;
-        le = cudaLaunchKernelEx(&cfg, decode_mma_kernel<T, kOcc, false, kNT>, p);
+        le = cudaLaunchKernelEx(&cfg, decode_mma_kernel<T, kOcc, false, kNT, kLean>, p);
     }
     count_launch();
     return check_cuda(le, "decode launch");
@@ -760,16 +703,19 @@ int launch_decode(const Layer& L, const void* x, int64_t ldx, void* y, int64_t l
         if (rc) { cudaFreeAsync(own, s); return rc; }
         ws = own;
     }
+    // the lean instance: one group per row, 32-byte aligned activation rows, K a multiple of 64 (tracing uses the generic one)
+    const bool lean = !g_trace && L.groups == 1 && (L.K & 63) == 0 && (ldx & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 31u) == 0;
+    const bool f16 = L.dtype == PBL_F16;
     int rc;
-    if (g.nt == 2)                                       // 9..16 tokens in one pass: 128 registers, 2 CTAs per SM
-        rc = (L.dtype == PBL_F16) ? launch_decode_t<__half, 2, 2>(L, x, ldx, y, ldy, M, ws, s)
-                                  : launch_decode_t<__nv_bfloat16, 2, 2>(L, x, ldx, y, ldy, M, ws, s);
-    else if (dk_occupancy() == 4)
-        rc = (L.dtype == PBL_F16) ? launch_decode_t<__half, 4, 1>(L, x, ldx, y, ldy, M, ws, s)
-                                  : launch_decode_t<__nv_bfloat16, 4, 1>(L, x, ldx, y, ldy, M, ws, s);
-    else
-        rc = (L.dtype == PBL_F16) ? launch_decode_t<__half, 3, 1>(L, x, ldx, y, ldy, M, ws, s)
-                                  : launch_decode_t<__nv_bfloat16, 3, 1>(L, x, ldx, y, ldy, M, ws, s);
+#define PBL_DK_LAUNCH(OCC, NT)                                                                                                 \
+    rc = lean ? (f16 ? launch_decode_t<__half, OCC, NT, true>(L, x, ldx, y, ldy, M, ws, s)                                     \
+                     : launch_decode_t<__nv_bfloat16, OCC, NT, true>(L, x, ldx, y, ldy, M, ws, s))                             \
+              : (f16 ? launch_decode_t<__half, OCC, NT, false>(L, x, ldx, y, ldy, M, ws, s)                                    \
+                     : launch_decode_t<__nv_bfloat16, OCC, NT, false>(L, x, ldx, y, ldy, M, ws, s))
+    if (g.nt == 2) { PBL_DK_LAUNCH(2, 2); }              // 9..16 tokens in one pass
+    else if (dk_occupancy() == 3) { PBL_DK_LAUNCH(3, 1); }
+    else { PBL_DK_LAUNCH(2, 1); }
+#undef PBL_DK_LAUNCH
     if (own) {
         const int rf = check_cuda(cudaFreeAsync(own, s), "cudaFreeAsync(decode workspace)");
         if (!rc) rc = rf;

@@ -1,59 +1,16 @@
 // Two-phase prefill path: expand the packed weight ONCE into a dense fp16/bf16 scratch (L2-resident for the
 // usual layer sizes), then run a plain tcgen05 CTA-pair GEMM with BOTH operands fed by TMA.
 //
-// The fused kernels (pbllm_gemm_tc*.cu) re-expand a weight tile for every token tile that uses it; that is
-// free when the tensor pipe is the bottleneck (M >= ~8k tokens) but makes 256 < M < 4k expansion-bound.
-// Here the expansion cost is paid once per weight per call (kernel 1, HBM/L2-write bound, ~2*N*K bytes),
-// and kernel 2 is an ordinary K-major x K-major GEMM: TMA (SWIZZLE_128B) for x and for the scratch,
-// cta_group::2 UMMA M=256 N=256, fp32 accumulators in TMEM, same epilogue as gemm_tc2_kernel.
-// The scratch holds exactly w_sim (bit-identical to unpack()), so results match the fused kernels bit for bit.
+// Kernel 1 is stream_unpack_kernel (pbllm_stream.cu): the expansion cost is paid once per weight per call
+// (L2-write bound, ~2*N*K bytes).  Kernel 2 is an ordinary K-major x K-major GEMM: TMA (SWIZZLE_128B) for x and
+// for the scratch, cta_group::2 UMMA M=256 N=256, fp32 accumulators in TMEM.
+// The scratch holds exactly w_sim (bit-identical to unpack()): with x = I the kernel reproduces w_sim^T bit for bit.
 #include <cstdlib>
 #include <type_traits>
 
 #include "pbllm_tc_ptx.cuh"
 
 namespace pbl {
-
-// ---- kernel 1: packed -> dense scratch [n_pad][k_pad], K contiguous ---------------------------------------
-// CTA = one 128x64 plane tile; thread = weight row: expand_row into a swizzled smem tile, then coalesced
-// 16 B stores (8 lanes per 128 B row).
-template <typename T>
-__global__ void __launch_bounds__(128) expand_dense_kernel(const uint4* __restrict__ planes, const uint32_t* __restrict__ vptr,
-                                                           const uint16_t* __restrict__ vals, const float2* __restrict__ affine,
-                                                           int tiles_c, int groups, int tiles_per_group, uint16_t* __restrict__ out,
-                                                           int64_t k_pad) {
-    __shared__ __align__(1024) uint8_t tile[kTileRows * 128];
-    __shared__ __align__(16) uint8_t scr[4][1024];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, r = threadIdx.x;
-    const int64_t t = blockIdx.x;
-    const int64_t tr = t / tiles_c, tc = t % tiles_c;
-    const uint4 pw = __ldg(planes + t * kTileRows + r);
-    const uint32_t cs = __ldg(vptr + t * kRgPerTile + wid), ce = __ldg(vptr + t * kRgPerTile + wid + 1);
-    const float2 a = __ldg(affine + (tr * kTileRows + r) * groups + tc / tiles_per_group);
-    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = make_uint4(0, 0, 0, 0);
-    {
-        const uint32_t b0 = (cs * 2u) & ~15u, b1 = ce * 2u;
-        const uint8_t* base = reinterpret_cast<const uint8_t*>(vals);
-        const uint32_t o0 = b0 + 16u * lane, o1 = o0 + 512u;
-        if (o0 < b1) v0 = __ldg(reinterpret_cast<const uint4*>(base + o0));
-        if (o1 < b1) v1 = __ldg(reinterpret_cast<const uint4*>(base + o1));
-    }
-    const uint32_t lo = bits16<T>(a.x), hi = bits16<T>(a.y);
-    const uint32_t tile_s = smem_u32(tile);
-    const uint32_t r7 = (uint32_t)(r & 7);
-    expand_row(pw, lo | (lo << 16), (lo ^ hi) * 0x10001u, tile_s + (uint32_t)r * 128u, r7, cs, ce, v0, v1, smem_u32(scr[wid]), vals,
-               (uint32_t)lane);
-    __syncthreads();
-    // copy out: 128 rows x 8 chunks of 16 B; consecutive threads take consecutive chunks of a row
-    uint16_t* dst = out + (tr * kTileRows) * k_pad + tc * kTileCols;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int idx = i * 128 + threadIdx.x;
-        const int row = idx >> 3, c = idx & 7;
-        const uint4 v = *reinterpret_cast<const uint4*>(tile + row * 128 + ((c ^ (row & 7)) << 4));
-        *reinterpret_cast<uint4*>(dst + (int64_t)row * k_pad + c * 8) = v;
-    }
-}
 
 namespace tt {
 constexpr int BMC = 256, BN = 256, BNC = 128, BK = 64;
@@ -248,26 +205,46 @@ gemm_tt_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
-static int twophase_mode() {   // PBL_TWOPHASE: 0 = never (fused kernels only), otherwise for every M > 128 (default)
-    const char* e = getenv("PBL_TWOPHASE");
-    return (e && *e) ? atoi(e) : 1;
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
 }
 
-bool gemm_twophase_enabled(const Layer& L, int64_t M) {
-    (void)L;
-    // measured faster than the fused CTA-pair kernel for every M > 256 on B200: 38 vs 49 us at M=512,
-    // 69 vs 94 us at M=2048, 389 vs 437 us at M=16384 (4096x4096), 1136 vs 1162 us (11008x4096)
-    return twophase_mode() != 0 && M > 128;
+// TMA boxes and the 16-byte epilogue stores need aligned, 8-element-multiple strides; anything else runs the decode
+// kernel in token passes
+bool gemm_twophase_supported(const Layer& L, const void* x, int64_t ldx, const void* y, int64_t ldy, int64_t M) {
+    if (L.dtype != PBL_F16 && L.dtype != PBL_BF16) return false;
+    if (!L.fsign) return false;
+    if (M <= 0 || M > (1 << 30)) return false;
+    if (L.N % 8 != 0 || ldy % 8 != 0 || ldx % 8 != 0) return false;
+    if (x && (reinterpret_cast<uintptr_t>(x) & 15u)) return false;
+    if (y && (reinterpret_cast<uintptr_t>(y) & 15u)) return false;
+    if (L.bias && (reinterpret_cast<uintptr_t>(L.bias) & 15u)) return false;
+    return true;
 }
 
 int launch_gemm_twophase(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled driver entry point unavailable"); return PBL_ERR_CUDA; }
-    static int num_sms = 0;
-    static bool pool_set = false;
+    static int sms_dev[64] = {};
+    static bool pool_set_dev[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!num_sms) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!sms_dev[dev]) cudaDeviceGetAttribute(&sms_dev[dev], cudaDevAttrMultiProcessorCount, dev);
+    const int num_sms = sms_dev[dev] > 0 ? sms_dev[dev] : 148;
+    bool& pool_set = pool_set_dev[dev];
     if (!pool_set) {   // keep freed scratch cached in the stream-ordered pool instead of returning it to the OS
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
@@ -283,15 +260,7 @@ int launch_gemm_twophase(const Layer& L, const void* x, int64_t ldx, void* y, in
     if (rc) return rc;
 
     const int which = L.dtype == PBL_F16 ? 0 : 1;
-    const unsigned tiles = (unsigned)(L.tiles_r * L.tiles_c);
-    if (which == 0)
-        expand_dense_kernel<__half><<<tiles, 128, 0, s>>>(L.planes, L.vptr, (const uint16_t*)L.vals, L.affine, (int)L.tiles_c,
-                                                         (int)L.groups, L.tiles_per_group, (uint16_t*)scratch, L.k_pad);
-    else
-        expand_dense_kernel<__nv_bfloat16><<<tiles, 128, 0, s>>>(L.planes, L.vptr, (const uint16_t*)L.vals, L.affine, (int)L.tiles_c,
-                                                                 (int)L.groups, L.tiles_per_group, (uint16_t*)scratch, L.k_pad);
-    count_launch();
-    rc = check_cuda(cudaGetLastError(), "expand_dense launch");
+    rc = launch_stream_unpack(L, scratch, L.k_pad, L.n_pad, L.k_pad, s);      // kernel 1: the exact w_sim, padded with level values
     if (rc) { cudaFreeAsync(scratch, s); return rc; }
 
     const int n_tiles = (int)((L.N + tt::BN - 1) / tt::BN);
@@ -316,7 +285,6 @@ int launch_gemm_twophase(const Layer& L, const void* x, int64_t ldx, void* y, in
         if (cr != CUDA_SUCCESS) { cudaFreeAsync(scratch, s); set_error("cuTensorMapEncodeTiled(w) failed (%d)", (int)cr); return PBL_ERR_CUDA; }
     }
     GemmParams p;
-    p.planes = L.planes; p.vptr = L.vptr; p.vals = reinterpret_cast<const uint16_t*>(L.vals); p.affine = L.affine;
     p.bias = L.bias; p.y = y; p.ldy = ldy; p.M = (int)M; p.N = (int)L.N; p.K = (int)L.K;
     p.tiles_r = (int)L.tiles_r; p.tiles_c = (int)L.tiles_c; p.groups = (int)L.groups; p.tiles_per_group = L.tiles_per_group;
     p.bm = bm;

@@ -170,87 +170,7 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t da, uint6
         : "memory");
 }
 
-// ---- the weight expansion shared by every tensor-core kernel ------------------------------------------------
-// Rebuild ONE weight row (64 exact 16-bit values = 128 B) of a 128B-swizzled K-major tile in shared memory:
-// sign bits -> byte-sign-replicating PRMT -> LOP3 select of the row's {lo,hi} pair (8 conflict-free STS.128),
-// then the row's salient values are patched over their positions.  Called by all 32 lanes of a warp, lane =
-// row of one 32-row group.
-//   pw      {sign[0:32], sign[32:64], salient[0:32], salient[32:64]} of this row
-//   LL, DD  {lo,lo} and {lo^hi, lo^hi} as packed 16-bit pairs
-//   brow    shared address of the row (128 B aligned);  r7 = row & 7 (swizzle key)
-//   cs, ce  the row group's value chunk [cs, ce) in `vals` (elements);  v0, v1 = this lane's prefetched 16 B
-//           slots (lane, lane+32) of the chunk counted from its 16 B-aligned start
-//   scratch the warp's private 1 KB staging buffer (512 values); values beyond it are read from `vals`
-__device__ __forceinline__ void expand_row(const uint4 pw, const uint32_t LL, const uint32_t DD, const uint32_t brow,
-                                           const uint32_t r7, const uint32_t cs, const uint32_t ce, const uint4 v0,
-                                           const uint4 v1, const uint32_t scratch, const uint16_t* __restrict__ vals,
-                                           const uint32_t lane) {
-    const uint32_t b0 = (cs * 2u) & ~15u;
-    const uint32_t npop = (uint32_t)(__popc(pw.z) + __popc(pw.w));
-    const bool any_sal = ce != cs;                       // warp-uniform (chunk bounds are per row group)
-    uint32_t idx0 = 0;
-    if (any_sal) {
-        __syncwarp();                                    // the previous item's scratch reads are finished
-        const uint32_t o0 = 16u * lane, o1 = o0 + 512u;
-        if (b0 + o0 < ce * 2u) sts_v4(scratch + o0, v0.x, v0.y, v0.z, v0.w);
-        if (b0 + o1 < ce * 2u) sts_v4(scratch + o1, v1.x, v1.y, v1.z, v1.w);
-        __syncwarp();                                    // staged values visible to every lane
-    }
-    // dense part: 64 bits -> 64 exact {lo,hi} values, 8 swizzled 16 B chunks
-#pragma unroll
-    for (int wd = 0; wd < 2; ++wd) {
-        const uint32_t sg = wd ? pw.y : pw.x;
-        const uint32_t X0 = sg, X1 = sg << 1, X2 = sg << 2, X3 = sg << 3, X4 = sg << 4, X5 = sg << 5, X6 = sg << 6, X7 = sg << 7;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const uint32_t sel = 0x8888u | (uint32_t)c | ((uint32_t)c << 4) | ((uint32_t)(4 + c) << 8) | ((uint32_t)(4 + c) << 12);
-            const uint32_t h0 = sel_xor_and(LL, DD, prmt(X7, X6, sel));
-            const uint32_t h1 = sel_xor_and(LL, DD, prmt(X5, X4, sel));
-            const uint32_t h2 = sel_xor_and(LL, DD, prmt(X3, X2, sel));
-            const uint32_t h3 = sel_xor_and(LL, DD, prmt(X1, X0, sel));
-            sts_v4(brow + ((((uint32_t)(wd * 4 + c)) ^ r7) << 4), h0, h1, h2, h3);
-        }
-    }
-    if (!any_sal) return;
-    idx0 = (cs - (b0 >> 1)) + warp_excl_scan(npop, lane);
-    // salient part: patch the exact stored values over their positions (a 2-way unrolled loop measured slower)
-    if (ce - (b0 >> 1) <= 512u) {                        // warp-uniform: the whole chunk is staged in scratch
-        uint32_t sa = scratch + idx0 * 2u;
-#pragma unroll
-        for (int wd = 0; wd < 2; ++wd) {
-            uint32_t rm = __brev(wd ? pw.w : pw.z);      // msb-first: clz gives the lowest column
-            const uint32_t k1 = (r7 << 4) ^ (uint32_t)(wd * 64);
-            while (rm) {
-                const uint32_t j = (uint32_t)__clz(rm);
-                rm &= ~(0x80000000u >> j);
-                const uint16_t v = lds_u16(sa);
-                sa += 2u;
-                sts_u16(brow | ((j + j) ^ k1), v);
-            }
-        }
-    } else {                                             // rare: very dense chunk, tail read from global
-        uint32_t idx = idx0;
-#pragma unroll
-        for (int wd = 0; wd < 2; ++wd) {
-            uint32_t mk = wd ? pw.w : pw.z;
-            while (mk) {
-                const uint32_t j = (uint32_t)__ffs(mk) - 1u;
-                mk &= mk - 1u;
-                uint16_t v;
-                if (idx < 512u) v = lds_u16(scratch + idx * 2u);
-                else v = __ldg(vals + (b0 >> 1) + idx);
-                ++idx;
-                sts_u16(brow + (((uint32_t)wd * 64u + (j << 1)) ^ (r7 << 4)), v);
-            }
-        }
-    }
-}
-
 struct GemmParams {
-    const uint4* planes;
-    const uint32_t* vptr;
-    const uint16_t* vals;
-    const float2* affine;
     const float* bias;
     void* y;
     int64_t ldy;
@@ -264,11 +184,5 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_fn();
-int launch_gemm_tc2(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s);
-bool gemm_tc2_enabled(const Layer& L, int64_t M);
-int launch_gemm_twophase(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s);
-bool gemm_twophase_enabled(const Layer& L, int64_t M);
-int launch_gemm_splitk(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s);
-bool gemm_splitk_supported(const Layer& L, const void* x, int64_t ldx, const void* y, int64_t ldy, int64_t M);
 
 }  // namespace pbl

@@ -98,7 +98,7 @@ class _PackedBase(nn.Module, BinaryInterface):
             return hit[1]
         with torch.no_grad():
             w = p.unpack().to(dtype)
-            low = None if p.nnz == 0 else p.low_mask_dense()
+            low = None if p.salient_count() == 0 else p.low_mask_dense()
             q = PackedLinear.from_dense(w, p.bias, low_mask=low, groupsize=p.groupsize)
         self._packed_cast[dtype] = (p, q)
         return q

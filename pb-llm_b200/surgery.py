@@ -158,13 +158,13 @@ def load_bnn(model, load_path):
 
 
 # ---- packed on-disk format: what save_bnn / save_pretrained only account for ----------------
-_PACKED_VERSION = 1
+_PACKED_VERSION = 2
 
 
 @torch.no_grad()
 def save_packed(model: nn.Module, save_path: str):
-    """Write every packed module's buffers (planes / vptr / vals / affine / bias) instead of 16-bit
-    latent or fake-quant weights: the checkpoint is as small as the model is in HBM (~3.6 bit/weight at
+    """Write every packed module's buffers (PackedLinear.buffers(): sign words / entries / affine / bias) instead of
+    16-bit latent or fake-quant weights: the checkpoint is as small as the model is in HBM (~4.3 bit/weight at
     low_frac 0.9) where the reference's save_bnn (utils.py:87-94) and save_pretrained
     (gptq_pb/run.py:315-319) store 16 bit/weight. meta.json keeps the reference's name -> class map."""
     os.makedirs(save_path, exist_ok=True)
@@ -173,11 +173,11 @@ def save_packed(model: nn.Module, save_path: str):
         if isinstance(m, BinaryInterface) and hasattr(m, "packed"):
             p = m.packed()
             meta["layers"][name] = {"cls": m.__class__.__name__, "N": p.N, "K": p.K, "groupsize": p.groupsize,
-                                    "dtype": str(p.dtype).replace("torch.", ""), "nnz": p.nnz,
+                                    "dtype": str(p.dtype).replace("torch.", ""), "flags": p.flags,
                                     "bias": p.bias is not None}
             for k, v in p.buffers().items():
                 if v is not None:
-                    tensors[f"{name}::{k}"] = (v[: p.nnz + 8] if k == "vals" else v).cpu()
+                    tensors[f"{name}::{k}"] = v.cpu()
     with open(os.path.join(save_path, "packed_meta.json"), "w") as f:
         json.dump(meta, f)
     torch.save(tensors, os.path.join(save_path, "packed_weights.pth"))
@@ -200,9 +200,10 @@ def load_packed(model: nn.Module, load_path: str, device=None):
         old = names[name]
         dev = device if device is not None else next(old.parameters()).device
         dt = getattr(torch, info["dtype"])
-        get = lambda k: tensors[f"{name}::{k}"].to(dev)  # noqa: E731
-        p = PackedLinear.from_buffers(info["N"], info["K"], info["groupsize"], dt, get("planes"), get("vptr"), get("vals"),
-                                      get("affine"), get("bias") if info["bias"] else None)
+        bufs = {k.split("::", 1)[1]: v.to(dev) for k, v in tensors.items() if k.startswith(name + "::")}
+        bias = bufs.pop("bias", None)
+        p = PackedLinear.from_buffers(info["N"], info["K"], info["groupsize"], dt, bufs, bias if info["bias"] else None,
+                                      info.get("flags", 0))
         cls = getattr(_quant, info["cls"])
         q = cls.__new__(cls)
         nn.Module.__init__(q)

@@ -55,13 +55,19 @@ def test_pack_sizes_host_only():
 
 def test_error_codes_without_compute():
     lib = _lib.load()
-    assert lib.pbl_abi_version() == 3
+    assert lib.pbl_abi_version() == 4
     assert lib.pbl_layer_create(None, None) == -1 and "null" in _lib.last_error()
     assert lib.pbl_linear_forward(None, None, 0, None, 0, 1, None) == -1
     assert lib.pbl_forward_host_workspace(None, 4) == 0
     assert lib.pbl_linear_forward_ws(None, None, 0, None, 0, 1, None, 0, None) == -1
     assert lib.pbl_decode_workspace_bytes(None, 8) == 0
-    assert lib.pbl_decode_index_sizes(None, None) == -1 and lib.pbl_layer_attach_decode_index(None, None, None, None) == -1
+    assert lib.pbl_stream_layout(4096, 4096, -1, 0, None) == -1 and lib.pbl_stream_position(0, 0, None) == -1
+    ss = _lib.PblStreamSizes()
+    assert lib.pbl_stream_layout(4096, 11008, -1, 0, C.byref(ss)) == 0
+    assert (ss.blocks, ss.fsign_bytes, ss.eptr_bytes) == (128 * 172, 4096 * 11008 // 8, (128 * 172 + 1) * 4)   # 1 bit / weight
+    assert lib.pbl_stream_layout(64, 64, -1, 2, C.byref(ss)) == -2 and "fp16" in _lib.last_error()             # fp32: planes layout
+    out4 = (C.c_uint32 * 4)()
+    assert lib.pbl_stream_position(32, 0, out4) == -3
     assert lib.pbl_launch_count() >= 0
 
 

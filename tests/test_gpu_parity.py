@@ -4,7 +4,8 @@ and -- at BASELINE.json's full layer sizes -- through size-independent propertie
 
 Tolerance (BASELINE.json north_star): 1e-3 relative, fp16. Written here as
     max|y - y_ref| / max|y_ref| <= 1e-3      (max-normalised; SURVEY.md 7 "Tolerance definition")
-for fp16/bf16 I/O (bf16 outputs round at 2^-9, so its bound is 4e-3), and 2e-5 for fp32 I/O.
+for fp16 I/O; 6e-3 for bf16 I/O (not a north-star dtype: its output rounds at 2^-9 and the salient weights are held in
+the layer's own 16-bit type in the kernel's +-1 units, a second 2^-9 rounding); 2e-5 for fp32 I/O.
 Packing is integer/bit work: unpack(pack(w)) must be bit-exact."""
 import ctypes as C
 import os
@@ -21,7 +22,7 @@ from oracle.gen_golden import make_weight, make_x
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 DEV = "cuda:0"
-TOL = {torch.float16: 1e-3, torch.bfloat16: 4e-3, torch.float32: 2e-5}
+TOL = {torch.float16: 1e-3, torch.bfloat16: 6e-3, torch.float32: 2e-5}
 
 
 def load(name):
@@ -46,8 +47,8 @@ def rms_rel(y, ref):
 
 
 def forced(p, x, kernel):
-    """Run p.forward with PBL_FORCE_KERNEL=kernel (0 CUDA cores, 1 tcgen05 GEMM, 2 mma.sync skinny, 3 split-K cluster,
-    4 decode kernel)."""
+    """Run p.forward with PBL_FORCE_KERNEL=kernel (0 CUDA cores (fp32 layers), 1 two-phase prefill: expansion + tcgen05
+    GEMM, 4 decode kernel in token passes)."""
     os.environ["PBL_FORCE_KERNEL"] = str(kernel)
     try:
         return p.forward(x)
@@ -67,7 +68,7 @@ def test_native_library_is_the_one_running():
     p = pb.PackedLinear.from_dense(torch.randn(64, 64, device=DEV, dtype=torch.float16).sign())
     p.forward(torch.randn(1, 64, device=DEV, dtype=torch.float16))
     torch.cuda.synchronize()
-    assert lib.pbl_launch_count() >= n0 + 5   # affine, planes, scan, vals, forward
+    assert lib.pbl_launch_count() >= n0 + 5   # affine, count, scan, fill, forward
 
 
 # ---- packing: bit-exact ------------------------------------------------------------------------
@@ -90,20 +91,26 @@ def test_pack_unpack_roundtrip_bit_exact(dtype, N, K, gs):
     wd = w.to(DEV)
     p = pb.PackedLinear.from_dense(wd, None, low_mask=low.to(DEV), groupsize=gs)
     assert torch.equal(p.unpack(), wd)
-    frac = p.nnz / (N * K)
+    frac = p.salient_count() / (N * K)
     assert 0.05 < frac < 0.2 or N * K < 4096
+    assert p.stream_layout == (dtype != torch.float32)
+    if p.stream_layout and N * K >= 4096:
+        # salient values far smaller than both levels cannot be written as level + 16-bit correction within 7 ulps: they
+        # must show up in the exception list (and still round-trip, asserted above)
+        assert p.n_exc > 0 and p.n_exc < 0.2 * p.salient_count()
     p2 = pb.PackedLinear.from_dense(wd, None, low_mask=None, groupsize=gs)   # mask-free: min/max levels only
     assert torch.equal(p2.unpack(), wd)
 
 
-def test_pack_levels_and_counts_against_numpy():
+def test_pack_planes_levels_and_counts_against_numpy():
+    """fp32 layers: the planes layout."""
     rs = np.random.RandomState(5)
     N, K = 200, 330
     w = np.where(rs.rand(N, K) < 0.5, 0.25, -0.5).astype(np.float32)
     sal = rs.rand(N, K) < 0.1
     w[sal] = rs.standard_normal(sal.sum()).astype(np.float32)
     p = pb.PackedLinear.from_dense(t(w), None, low_mask=t(~sal))
-    assert p.nnz == int(sal.sum())
+    assert p.nnz == int(sal.sum()) and not p.stream_layout
     aff = p.affine.view(-1, 2).cpu().numpy()
     assert np.array_equal(aff[:N, 0], np.full(N, -0.5, np.float32)) and np.array_equal(aff[:N, 1], np.full(N, 0.25, np.float32))
     assert np.array_equal(aff[N:], np.zeros_like(aff[N:]))
@@ -178,18 +185,20 @@ def test_forward_shapes_strides_and_errors():
     assert lib.pbl_linear_forward(p.handle, C.c_void_p(x.data_ptr()), 100, C.c_void_p(y.data_ptr()), 96, 4, None) == -3
 
 
-# ---- tcgen05 GEMM path (M above the skinny-kernel threshold) ---------------------------------------
+# ---- two-phase prefill path (M above PBL_DECODE_MAX_M): expansion + tcgen05 GEMM ---------------------------------
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("N,K,gs,M,bias", [(256, 64, -1, 16, False), (256, 256, -1, 128, True), (256, 256, -1, 129, False),
                                            (264, 520, -1, 300, True), (768, 768, -1, 1000, True), (512, 1024, 256, 37, False),
                                            (128, 4096, -1, 256, False), (1024, 11008, -1, 64, False),
-                                           (4096, 4096, -1, 512, False)])
-def test_gemm_tc_matches_oracle(dtype, N, K, gs, M, bias):
+                                           (4096, 4096, -1, 512, False), (264, 520, -1, 700, True), (512, 1024, 256, 513, False),
+                                           (1024, 4096, -1, 2048, False), (4096, 4096, -1, 2560, False), (1024, 11008, -1, 600, True)])
+def test_prefill_gemm_matches_oracle(dtype, N, K, gs, M, bias):
+    """expand-once + TMA/TMA tcgen05 GEMM (cta_group::2), incl. ragged M/N/K, groups, single-CTA-valid tiles."""
     w, low = synth_wsim(N, K, gs, dtype, seed=N + K + M)
     b = rounded(np.random.RandomState(2).standard_normal(N).astype(np.float32) * 0.1, dtype) if bias else None
     x = rounded(make_x(N * 3 + M, (M, K)), dtype)
     p = pb.PackedLinear.from_dense(t(w, dtype), None if b is None else t(b, dtype), t(low), gs)
-    assert p.select_kernel(M) == (4 if M <= 16 else (3 if M <= 128 else 1))   # decode / split-K cluster / GEMM
+    assert p.select_kernel(M) == (4 if M <= 64 else 1)               # decode kernel in token passes / prefill GEMM
     y = forced(p, t(x, dtype), 1)
     if M * N * K <= 4e8:
         ref = orc.linear(x, w, b)                                   # CPU oracle (double accumulate)
@@ -197,124 +206,22 @@ def test_gemm_tc_matches_oracle(dtype, N, K, gs, M, bias):
         ref = (t(x).double() @ t(w).double().t() + (0 if b is None else t(b).double())).cpu().numpy()
     assert relmax(y, ref) <= TOL[dtype], (relmax(y, ref), rms_rel(y, ref))
     assert rms_rel(y, ref) <= TOL[dtype]
-    y0 = forced(p, t(x, dtype), 0)                                  # all kernels agree on the same packed layer
-    assert relmax(y, y0.float().cpu().numpy()) <= 2 * TOL[dtype]
-    if M <= 300:
-        y2 = forced(p, t(x, dtype), 2)
-        assert relmax(y2, ref) <= TOL[dtype]
+    assert torch.equal(y, forced(p, t(x, dtype), 1))                # deterministic
+    if M <= 300:                                                    # both kernels agree on the same packed layer
+        y4 = forced(p, t(x, dtype), 4)
+        assert relmax(y4, ref) <= TOL[dtype]
 
 
-@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("N,K,gs,M,bias", [(128, 64, -1, 1, False), (96, 160, -1, 3, True), (100, 70, -1, 5, False),
-                                           (300, 520, -1, 8, True), (256, 512, 128, 2, False), (768, 768, -1, 1, True),
-                                           (33, 2048, -1, 9, False), (512, 1024, 256, 16, True), (4096, 4096, -1, 8, False),
-                                           (1024, 11008, -1, 7, False), (264, 1030, -1, 17, True)])
-def test_skinny_mma_matches_oracle(dtype, N, K, gs, M, bias):
-    """mma.sync bit-plane kernel (decode regime), incl. ragged N/K, odd leading dims, groups."""
-    w, low = synth_wsim(N, K, gs, dtype, seed=N + K + M)
-    b = rounded(np.random.RandomState(3).standard_normal(N).astype(np.float32) * 0.1, dtype) if bias else None
-    x = rounded(make_x(N * 5 + M, (M, K)), dtype)
-    p = pb.PackedLinear.from_dense(t(w, dtype), None if b is None else t(b, dtype), t(low), gs)
-    assert p.select_kernel(min(M, 16)) == 4          # default route; the skinny kernel stays reachable when forced
-    y = forced(p, t(x, dtype), 2)
-    ref = orc.linear(x, w, b) if M * N * K <= 4e8 else \
-        (t(x).double() @ t(w).double().t() + (0 if b is None else t(b).double())).cpu().numpy()
-    assert relmax(y, ref) <= TOL[dtype], (relmax(y, ref), rms_rel(y, ref))
-    assert rms_rel(y, ref) <= TOL[dtype]
-    assert torch.equal(y, forced(p, t(x, dtype), 2))                # deterministic reduction
-    y0 = forced(p, t(x, dtype), 0)
-    assert relmax(y, y0.float().cpu().numpy()) <= 2 * TOL[dtype]
-
-
-@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("N,K,gs,M,bias", [(256, 64, -1, 16, False), (256, 256, -1, 300, True), (264, 520, -1, 700, True),
-                                           (768, 768, -1, 1000, True), (512, 1024, 256, 513, False),
-                                           (1024, 4096, -1, 2048, False), (4096, 4096, -1, 2560, False)])
-def test_gemm_tc_cta_pair_matches_oracle(dtype, N, K, gs, M, bias):
-    """cta_group::2 kernel (SM pairs), forced on for every shape incl. ragged M/N/K and single-CTA-valid tiles."""
-    w, low = synth_wsim(N, K, gs, dtype, seed=N + K + M)
-    b = rounded(np.random.RandomState(4).standard_normal(N).astype(np.float32) * 0.1, dtype) if bias else None
-    x = rounded(make_x(N * 11 + M, (M, K)), dtype)
-    p = pb.PackedLinear.from_dense(t(w, dtype), None if b is None else t(b, dtype), t(low), gs)
-    os.environ["PBL_GEMM_2CTA"] = "2"
-    try:
-        y = forced(p, t(x, dtype), 1)
-    finally:
-        os.environ.pop("PBL_GEMM_2CTA")
-    ref = orc.linear(x, w, b) if M * N * K <= 4e8 else \
-        (t(x).double() @ t(w).double().t() + (0 if b is None else t(b).double())).cpu().numpy()
-    assert relmax(y, ref) <= TOL[dtype], (relmax(y, ref), rms_rel(y, ref))
-    os.environ["PBL_GEMM_2CTA"] = "0"
-    try:
-        y1 = forced(p, t(x, dtype), 1)
-    finally:
-        os.environ.pop("PBL_GEMM_2CTA")
-    assert torch.equal(y, y1)                                       # same tile, same k order: bit-identical to the 1-CTA kernel
-
-
-@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("N,K,gs,M,bias", [(256, 64, -1, 1, False), (256, 256, -1, 8, True), (264, 520, -1, 16, True),
-                                           (100, 70, -1, 5, False), (768, 768, -1, 33, True), (512, 1024, 256, 64, False),
-                                           (4096, 4096, -1, 8, False), (11008, 4096, -1, 8, False), (4096, 11008, -1, 128, True),
-                                           (1024, 4096, -1, 100, False)])
-def test_gemm_splitk_cluster_matches_oracle(dtype, N, K, gs, M, bias):
-    """tcgen05 split-K cluster kernel (DSMEM reduction), incl. ragged shapes, every cluster size."""
-    w, low = synth_wsim(N, K, gs, dtype, seed=N + K + M)
-    b = rounded(np.random.RandomState(5).standard_normal(N).astype(np.float32) * 0.1, dtype) if bias else None
-    x = rounded(make_x(N * 13 + M, (M, K)), dtype)
-    p = pb.PackedLinear.from_dense(t(w, dtype), None if b is None else t(b, dtype), t(low), gs)
-    ref = orc.linear(x, w, b) if M * N * K <= 4e8 else \
-        (t(x).double() @ t(w).double().t() + (0 if b is None else t(b).double())).cpu().numpy()
-    if K % 8 != 0:   # TMA needs 16 B-aligned activation rows: the forced kernel is refused, never silently replaced
-        with pytest.raises(RuntimeError, match="does not support"):
-            forced(p, t(x, dtype), 3)
-        assert p.select_kernel(M) == 4
-        return
-    assert p.select_kernel(M) == (4 if M <= 16 else 3)
-    ys = []
-    for C in ("", "1", "2", "3", "5", "8"):
-        if C:
-            os.environ["PBL_SPLITK_C"] = C
-        try:
-            y = forced(p, t(x, dtype), 3)
-        finally:
-            os.environ.pop("PBL_SPLITK_C", None)
-        assert relmax(y, ref) <= TOL[dtype], (C, relmax(y, ref))
-        ys.append(y)
-    assert torch.equal(ys[0], forced(p, t(x, dtype), 3))            # deterministic reduction order
-
-
-@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("N,K,gs,M,bias", [(256, 64, -1, 300, False), (264, 520, -1, 700, True), (768, 768, -1, 1000, True),
-                                           (512, 1024, 256, 513, False), (4096, 4096, -1, 2048, False), (1024, 11008, -1, 600, True)])
-def test_gemm_two_phase_matches_fused(dtype, N, K, gs, M, bias):
-    """expand-once + TMA/TMA GEMM: the scratch is exactly w_sim, so results equal the fused kernels bit for bit."""
-    w, low = synth_wsim(N, K, gs, dtype, seed=N + K + M)
-    b = rounded(np.random.RandomState(6).standard_normal(N).astype(np.float32) * 0.1, dtype) if bias else None
-    x = rounded(make_x(N * 17 + M, (M, K)), dtype)
-    p = pb.PackedLinear.from_dense(t(w, dtype), None if b is None else t(b, dtype), t(low), gs)
-    ref = orc.linear(x, w, b) if M * N * K <= 4e8 else \
-        (t(x).double() @ t(w).double().t() + (0 if b is None else t(b).double())).cpu().numpy()
-    outs = {}
-    for mode in ("2", "0"):
-        os.environ["PBL_TWOPHASE"] = mode
-        try:
-            outs[mode] = forced(p, t(x, dtype), 1)
-        finally:
-            os.environ.pop("PBL_TWOPHASE")
-        assert relmax(outs[mode], ref) <= TOL[dtype], (mode, relmax(outs[mode], ref))
-    assert torch.equal(outs["2"], outs["0"])
-
-
-def test_gemm_tc_one_hot_activations_reproduce_w_sim_exactly():
-    """x = I  =>  y = w_sim^T bit-for-bit: the expanded tile IS the reference's tensor."""
+def test_prefill_one_hot_activations_reproduce_w_sim_exactly():
+    """x = I  =>  y = w_sim^T bit-for-bit: the expanded scratch IS the reference's tensor."""
     w, low = synth_wsim(512, 256, -1, torch.float16, 77)
     p = pb.PackedLinear.from_dense(t(w, torch.float16), None, t(low))
     y = p.forward(torch.eye(256, device=DEV, dtype=torch.float16))
     assert p.select_kernel(256) == 1
     assert torch.equal(y, t(w, torch.float16).t())
-    y2 = forced(p, torch.eye(256, device=DEV, dtype=torch.float16), 2)   # register-built fragments: same exact tile
-    assert torch.equal(y2, t(w, torch.float16).t())
+    # the decode kernel sums level + correction in fp32: within an ulp or two of w_sim, not bit-identical
+    y4 = forced(p, torch.eye(256, device=DEV, dtype=torch.float16), 4)
+    assert relmax(y4, w.T) <= 1e-3
 
 
 # ---- golden fixtures from the executed reference --------------------------------------------------
@@ -379,7 +286,7 @@ def test_golden_outlier_drop_in_ctor(tag):
     assert relmax(y, ref) <= TOL[dtype]
     assert abs(m.outlier_nbits - float(g["nbits"])) < 1e-12
     p = m.packed()
-    assert p.nnz >= int(g["mask"].sum())
+    assert p.salient_count() >= int(g["mask"].sum())
     reg = m.to_regular_linear()
     assert torch.equal(reg.weight.data, m.dense_weight())
     m.pack(keep_latent=False)
@@ -400,7 +307,7 @@ def test_golden_outlier_768_known_answers():
     p = m.packed()
     aff = p.affine.view(-1, 2)[:768].cpu().numpy()
     assert np.all(aff[:, 0] == 0.0) and np.allclose(aff[:, 1], float(g["binary_scale"]), rtol=1e-6)  # levels {0, alpha}
-    assert p.nnz == 58982                                           # zeros are a LEVEL here, not residual
+    assert p.nnz == 58982 and not p.stream_layout                  # fp32 module: planes layout; zeros are a LEVEL here
 
 
 def test_golden_hessian_mask(tmp_path, monkeypatch):
@@ -436,7 +343,7 @@ def test_golden_gptqpb_fakequant_layers(tag):
     assert torch.equal(m.dense_weight(), lin.weight.data)           # exact weights, only the sum order differs
     p = m.packed()
     sal = int((~g["low_mask"]).sum())
-    assert sal <= p.nnz <= sal + 0.01 * g["Wq"].size               # + rare third value mu (sign(0))
+    assert sal <= p.salient_count() <= sal + 0.01 * g["Wq"].size   # + rare third value mu (sign(0))
     m2 = pb.PackedFakeQuantLinear.from_linear(lin, None, gs)       # no mask file: levels from min/max
     assert relmax(m2(t(g["x"])), g["y"]) <= 1e-3
 
@@ -464,7 +371,8 @@ def test_full_size_properties_llama7b_shapes(N, K, M):
     w = torch.where(low, w, (torch.randn(N, K, device=DEV, generator=gen) * 0.03).half())
     p = pb.PackedLinear.from_dense(w, None, low)
     assert torch.equal(p.unpack(), w)                               # round trip at full size
-    assert abs(p.nnz / (N * K) - 0.1) < 0.005
+    assert abs(p.salient_count() / (N * K) - 0.1) < 0.005
+    assert p.bits_per_weight() < 4.5                                # every resident byte: sign plane + 32-bit entries + tables
     x1 = torch.randn(M, K, device=DEV, generator=gen).half()
     x2 = torch.randn(M, K, device=DEV, generator=gen).half()
     y1, y2 = p.forward(x1).float(), p.forward(x2).float()
@@ -493,37 +401,29 @@ def test_full_size_outlier_module_opt13b_shapes(N, K):
     assert torch.equal(w_sim, m.binarize_except_outliers())                             # packed form == reference tensor
     ref = x.double().view(-1, K) @ w_sim.double().t() + b.double()
     assert float((y.double().view(-1, N) - ref).abs().max() / ref.abs().max()) <= 1e-3
-    y1 = m(x[:, :1])                                                                    # decode-sized call, skinny kernel
+    y1 = m(x[:, :1])                                                                    # decode-sized call, decode kernel
     assert float((y1.double().view(-1, N) - ref[:1]).abs().max() / ref[:1].abs().max()) <= 1e-3
-    assert 1.0 < m.outlier_nbits < 2.0 and m.packed().bits_per_weight() < 4.0
+    assert 1.0 < m.outlier_nbits < 2.0 and m.packed().bits_per_weight() < 4.6
 
 
 # ---- stress the rarely-taken paths of the expansion / packing -----------------------------------------------------
 @pytest.mark.parametrize("sal_frac", [0.0, 0.35, 0.6, 1.0])
 @pytest.mark.parametrize("M", [4, 40, 300, 700])
-def test_dense_salient_chunks_all_kernels(sal_frac, M):
-    """Salient density from none to every position: chunks larger than the 512-value staging buffer take the
-    global-memory tail path of expand_row; every kernel (skinny / split-K / GEMM / CTA pair) must still be exact."""
+def test_dense_salient_blocks_all_kernels(sal_frac, M):
+    """Salient density from none to every position: blocks with more than 256 entries take the in-loop entry loads of the
+    decode kernel (patch and un-patch); every kernel must still be within tolerance and unpack exact."""
     N, K, dtype = 320, 704, torch.float16
     w, low = synth_wsim(N, K, -1, dtype, seed=int(sal_frac * 100) + M, sal_frac=sal_frac)
     x = rounded(make_x(M + 17, (M, K)), dtype)
     p = pb.PackedLinear.from_dense(t(w, dtype), None, t(low))
     assert torch.equal(p.unpack(), t(w, dtype))
-    assert abs(p.nnz / (N * K) - sal_frac) < 0.02
+    assert abs(p.salient_count() / (N * K) - sal_frac) < 0.02
     ref = orc.linear(x, w)
     y = p.forward(t(x, dtype))
     assert relmax(y, ref) <= 1e-3, (p.select_kernel(M), relmax(y, ref))
-    os.environ["PBL_GEMM_2CTA"] = "2"
-    try:
-        assert relmax(forced(p, t(x, dtype), 1), ref) <= 1e-3
-    finally:
-        os.environ.pop("PBL_GEMM_2CTA")
-    if M <= 128:
-        assert relmax(forced(p, t(x, dtype), 3), ref) <= 1e-3
-    if M <= 40:
-        assert relmax(forced(p, t(x, dtype), 2), ref) <= 1e-3
-        assert relmax(forced(p, t(x, dtype), 0), ref) <= 1e-3
-        assert relmax(forced(p, t(x, dtype), 4), ref) <= 1e-3      # > 256 salient per block: the in-loop entry loads
+    assert relmax(forced(p, t(x, dtype), 1), ref) <= 1e-3
+    if M <= 300:
+        assert relmax(forced(p, t(x, dtype), 4), ref) <= 1e-3
 
 
 def test_degenerate_rows_and_levels():
@@ -541,52 +441,92 @@ def test_degenerate_rows_and_levels():
         p = pb.PackedLinear.from_dense(t(w, torch.float16), None, None, gs)
         assert torch.equal(p.unpack(), t(w, torch.float16))
         ref = orc.linear(x, w)
-        for kern in (0, 2, 3, 1, 4):
+        for kern in (1, 4):
             assert relmax(forced(p, t(x, torch.float16), kern), ref) <= 1e-3, (gs, kern)
 
 
-# ---- the decode kernel (pbl_select_kernel == 4): positioned salient entries, warp-granular stream-K ----------------
-def decode_index_to_dense(p):
-    """Rebuild w_sim from the decode index alone (dsign + eptr + ent + affine), on the host."""
+# ---- the block-stream layout and the decode kernel (pbl_select_kernel == 4) ------------------------------------------
+def bits16_to_f32(b, dtype):
+    b = np.asarray(b, np.uint32)
+    if dtype == torch.float16:
+        return b.astype(np.uint16).view(np.float16).astype(np.float32)
+    return (b << 16).view(np.float32)
+
+
+def f32_to_bits16(v, dtype):
+    tt = torch.from_numpy(np.ascontiguousarray(v, np.float32)).to(dtype)
+    return tt.view(torch.int16).numpy().astype(np.uint32) & 0xFFFF
+
+
+def stream_to_dense(p):
+    """Rebuild w_sim from the block stream alone (fsign + eptr + ent + exc + affine) on the host, following
+    csrc/pbllm_stream.cuh: level from the fragment-ordered sign bit, salient value = step(fl16(mid + half * tau), k)."""
+    lib = _lib.load()
+    out4 = (C.c_uint32 * 4)()
+    pos = np.zeros((32, 64, 4), np.int64)
+    for r in range(32):
+        for c in range(64):
+            lib.pbl_stream_position(r, c, out4)
+            pos[r, c] = list(out4)
+    slot_r, slot_c = np.zeros(2048, np.int64), np.zeros(2048, np.int64)
+    slot_r[pos[..., 3].ravel()] = np.repeat(np.arange(32), 64)
+    slot_c[pos[..., 3].ravel()] = np.tile(np.arange(64), 32)
     TC, rgs = int(p.sizes.tiles_c), int(p.sizes.n_pad) // 32
     G = int(p.sizes.groups)
     tpg = TC if G == 1 else p.groupsize // 64
-    dsign = p.dsign.cpu().numpy().view(np.uint32).reshape(rgs * TC, 32, 2)
+    fsign = p.fsign.cpu().numpy().view(np.uint32).reshape(rgs * TC, 32, 2)
     eptr = p.eptr.cpu().numpy().view(np.uint32)
     ent = p.ent.cpu().numpy().view(np.uint32)
     aff = p.affine.cpu().numpy().reshape(int(p.sizes.n_pad), G, 2)
-    npdt = np.float16 if p.dtype == torch.float16 else None
     out = np.zeros((rgs * 32, TC * 64), np.float32)
+
+    def ord16(b):
+        b = b.astype(np.int64)
+        return np.where(b & 0x8000, -(b & 0x7FFF), b & 0x7FFF)
+
     for blk in range(rgs * TC):
         rg, kb = divmod(blk, TC)
         g = kb // tpg
-        bits = ((dsign[blk][:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(32, 64)
+        low = (fsign[blk][pos[..., 0], pos[..., 1]] >> pos[..., 2].astype(np.uint32)) & 1          # [32][64], 1 = LOW level
         lo, hi = aff[rg * 32:rg * 32 + 32, g, 0:1], aff[rg * 32:rg * 32 + 32, g, 1:2]
-        tile = np.where(bits == 1, hi, lo).astype(np.float32)
+        tile = np.where(low == 1, lo, hi).astype(np.float32)
         e = ent[eptr[blk] * 4:eptr[blk + 1] * 4]
-        pos, val = e >> 16, (e & 0xFFFF).astype(np.uint16)
-        r = pos // 128                                    # tile layout of pbllm_decode.cu: chunk pc, word t, half e
-        pc = ((pos % 128) // 16) ^ (r & 7)                # <-> logical column 16 t + 2 pc + e
-        col = 16 * ((pos % 16) // 4) + 2 * pc + (pos % 4) // 2
-        if npdt is not None:
-            v = val.view(np.float16).astype(np.float32)
-        else:
-            v = (val.astype(np.uint32) << 16).view(np.float32)
-        tile[r, col] = v
+        if len(e):
+            slot, k4, tau16 = (e >> 21).astype(np.int64), ((e >> 16) & 15).astype(np.int64), e & 0xFFFF
+            k = np.where(k4 & 8, k4 - 16, k4)
+            r, c = slot_r[slot], slot_c[slot]
+            lo32, hi32 = lo[r, 0].astype(np.float32), hi[r, 0].astype(np.float32)
+            mid, half = np.float32(0.5) * (lo32 + hi32), np.float32(0.5) * (hi32 - lo32)
+            s = (half.astype(np.float64) * bits16_to_f32(tau16, p.dtype).astype(np.float64) + mid.astype(np.float64)).astype(np.float32)  # fma
+            n = ord16(f32_to_bits16(s, p.dtype)) + k
+            vb = np.where(n < 0, 0x8000 | (-n), n).astype(np.uint32)
+            keep = k != -8
+            tile[r[keep], c[keep]] = bits16_to_f32(vb[keep], p.dtype)
         out[rg * 32:rg * 32 + 32, kb * 64:kb * 64 + 64] = tile
+    if p.n_exc:
+        exc = p.exc.cpu().numpy().view(np.uint32).reshape(-1, 2)[: p.n_exc]
+        rg, kb = np.divmod(exc[:, 0].astype(np.int64), TC)
+        sl = (exc[:, 1] >> 16).astype(np.int64)
+        out[rg * 32 + slot_r[sl], kb * 64 + slot_c[sl]] = bits16_to_f32(exc[:, 1] & 0xFFFF, p.dtype)
     return out[:p.N, :p.K]
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("N,K,gs", [(128, 64, -1), (100, 70, -1), (300, 520, -1), (256, 512, 128), (33, 2048, -1)])
-def test_decode_index_reproduces_w_sim_bit_exactly(dtype, N, K, gs):
+def test_stream_layout_reproduces_w_sim_bit_exactly(dtype, N, K, gs):
     w, low = synth_wsim(N, K, gs, dtype, seed=N + K)
+    w[::7, ::5] = rounded(np.float32(w[::7, ::5]) * 1e-3, dtype)          # tiny salient values: ulp corrections and exceptions
+    low[::7, ::5] = False
     p = pb.PackedLinear.from_dense(t(w, dtype), None, t(low), gs)
-    assert p.ent is not None and p.decode_index_bytes() > 0
+    assert p.stream_layout and p.packed_bytes() > 0
     eptr = p.eptr.cpu().numpy().view(np.uint32)
+    nnz = p.salient_count()
     assert eptr[0] == 0 and np.all(np.diff(eptr.astype(np.int64)) >= 0)
-    assert int(eptr[-1]) * 4 >= p.nnz and int(eptr[-1]) * 4 <= p.nnz + 3 * (len(eptr) - 1)      # padded to 4 per block
-    assert np.array_equal(decode_index_to_dense(p), w)                                         # integer / bit work: exact
+    assert int(eptr[-1]) * 4 >= nnz and int(eptr[-1]) * 4 <= nnz + 3 * (len(eptr) - 1)          # padded to 4 per block
+    assert nnz == int((~low).sum()) and p.n_exc > 0
+    assert np.array_equal(stream_to_dense(p), w)                                               # integer / bit work: exact
+    assert torch.equal(p.unpack(), t(w, dtype))
+    assert torch.equal(p.low_mask_dense().cpu(), torch.from_numpy(low))
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
@@ -610,8 +550,6 @@ def test_decode_kernel_matches_oracle(dtype, N, K, gs, M, bias):
     assert rms_rel(y, ref) <= TOL[dtype]
     for _ in range(3):
         assert torch.equal(y, p.forward(t(x, dtype)))                # deterministic: slots are summed in CTA order
-    y2 = forced(p, t(x, dtype), 2)                                   # same exact tile, other summation order
-    assert relmax(y, y2.float().cpu().numpy()) <= 2 * TOL[dtype]
 
 
 def test_decode_kernel_workspace_sharing_and_graph():
@@ -660,14 +598,10 @@ def test_decode_kernel_workspace_sharing_and_graph():
     rc = lib.pbl_linear_forward_ws(p.handle, xs[p.K].data_ptr(), p.K, yg.data_ptr(), p.N, 8, small.data_ptr(), small.numel(),
                                    torch.cuda.current_stream().cuda_stream)
     assert rc == -3 and "workspace" in _lib.last_error()
-    # without a decode index the call falls back to the skinny kernel
-    p.drop_decode_index()
-    assert p.select_kernel(8) == 2
-    assert relmax(p.forward(xs[p.K]), outs[1].float().cpu().numpy()) <= 2e-3
 
 
-def test_decode_index_entry_order_spreads_banks():
-    """The index builder deals a block's entries to the kernel's 8 patch stores by shared-memory bank: with <= 8
+def test_stream_entry_order_spreads_banks():
+    """The packer deals a block's entries to the kernel's 8 patch stores by shared-memory bank: with <= 8
     entries per bank every store is conflict free; at 10 % density the average store must need well under the ~3
     wavefronts of the row-major order."""
     w, low = synth_wsim(256, 512, -1, torch.float16, seed=5)
@@ -683,8 +617,8 @@ def test_decode_index_entry_order_spreads_banks():
         h1 = (n4 + 1) // 2
         for units in (e[:h1], e[h1:]):
             for j in range(4):
-                pos = units[:, j] >> 16
-                words = np.unique(pos // 4)                      # lanes writing the same word do not conflict
+                slot = units[:, j] >> 21                         # 16-bit slot; two slots per 32-bit word
+                words = np.unique(slot // 2)                     # lanes writing the same word do not conflict
                 waves += np.bincount(words % 32).max()
                 stores += 1
     assert stores > 0 and waves / stores < 2.4, waves / stores

@@ -65,12 +65,12 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.reps
     nk = sum(p.N * p.K for p, _ in layers)
-    nnz = sum(p.nnz for p, _ in layers)
+    nnz = sum(p.salient_count() for p, _ in layers)
     alg = nk / 8 + 4 * sum(p.N for p, _ in layers) + 2 * M * sum(p.K + p.N for p, _ in layers) + 2 * nnz + sum(p.N + 1 for p, _ in layers)
     print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("PBL_")}, "kernel": layers[0][0].select_kernel(M),
                       "layers": a.layers, "batch": M, "ms": ms, "ms_per_32_layers": ms * 32 / a.layers,
                       "us_per_launch": ms * 1e3 / len(layers), "alg_gbs": alg / ms / 1e6, "max_rel_err": err,
-                      "index_gbs": sum(p.decode_index_bytes() for p, _ in layers) / ms / 1e6}))
+                      "packed_gbs": sum(p.packed_bytes() for p, _ in layers) / ms / 1e6}))
 
 
 if __name__ == "__main__":
