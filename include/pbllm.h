@@ -182,6 +182,27 @@ PBL_API size_t pbl_decode_workspace_bytes(const pbl_layer* layer, int64_t M);
 PBL_API int pbl_linear_forward_ws(const pbl_layer* layer, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M,
                                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- row-sharded execution across the GPUs of a node: rank g holds the packed rows [g*N/G, (g+1)*N/G) of a
+ *      linear, x is replicated, and the all-gather of the [M, N/G] slices is FUSED into the decode kernel: its epilogue
+ *      stores the slice straight into the y buffer of every rank through peer-mapped pointers (NVLink / NVSwitch), the last
+ *      CTA of the grid publishes a new epoch in every rank's flag array, and the next pushed kernel (or pbl_peer_wait)
+ *      waits until the flags of all ranks show the previous push.  No NCCL call on the per-token path.
+ *      M <= 16 (one decode pass); larger calls gather with the caller's collective library. ---- */
+#define PBL_MAX_PEERS 8
+typedef struct {
+    void* y[PBL_MAX_PEERS];         /* y [M][ldy] of every rank, peer-mapped, already offset to THIS rank's first output column */
+    uint32_t* flags[PBL_MAX_PEERS]; /* flag array u32 [PBL_MAX_PEERS] of every rank, peer-mapped, zero-initialised once */
+    uint32_t* sync_ctr;             /* local device u32 [2], zero-initialised once; shared by all pushed layers of this rank */
+    int32_t n_ranks, rank;
+    int32_t wait_prev;              /* nonzero: wait for every rank's previous push before reading x (x was produced by it) */
+    int32_t reserved;
+} pbl_peer_push;
+PBL_API int pbl_linear_forward_push(const pbl_layer* layer, const void* x, int64_t ldx, const pbl_peer_push* push, int64_t ldy,
+                                    int64_t M, void* workspace, size_t workspace_bytes, void* stream);
+/* Stream-ordered wait until every rank's latest push has landed in this rank's buffers (for consumers that are not
+ * pushed kernels, and for the end of a timed step). */
+PBL_API int pbl_peer_wait(const pbl_peer_push* push, void* stream);
+
 /* Host-only: the decode kernel's launch plan for an N x K layer, M tokens, on a device with `sms` SMs and
  * `ctas_per_sm` CTAs of 8 warps per SM (a pass handles 8 tokens, or 16 when M > 8).  out8 = {blocks, row groups, grid.x,
  * token passes, q, rem, slots, workspace KiB}:

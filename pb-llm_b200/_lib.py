@@ -24,6 +24,14 @@ class PblLayerDesc(C.Structure):
                 ("fsign", C.c_void_p), ("eptr", C.c_void_p), ("ent", C.c_void_p), ("exc", C.c_void_p), ("n_exc", C.c_int64)]
 
 
+MAX_PEERS = 8
+
+
+class PblPeerPush(C.Structure):
+    _fields_ = [("y", C.c_void_p * MAX_PEERS), ("flags", C.c_void_p * MAX_PEERS), ("sync_ctr", C.c_void_p),
+                ("n_ranks", C.c_int32), ("rank", C.c_int32), ("wait_prev", C.c_int32), ("reserved", C.c_int32)]
+
+
 class PblStreamSizes(C.Structure):
     _fields_ = [("blocks", C.c_int64), ("fsign_bytes", C.c_size_t), ("eptr_bytes", C.c_size_t)]
 
@@ -50,6 +58,9 @@ SYMBOLS = {
     "pbl_stream_fill": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pbl_stream_position": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_uint32)]),
+    "pbl_linear_forward_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(PblPeerPush), C.c_int64, C.c_int64,
+                                          C.c_void_p, C.c_size_t, C.c_void_p]),
+    "pbl_peer_wait": (C.c_int, [C.POINTER(PblPeerPush), C.c_void_p]),
     "pbl_decode_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64]),
     "pbl_decode_set_trace": (None, [C.c_void_p, C.c_size_t]),
     "pbl_decode_plan": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_uint32)]),

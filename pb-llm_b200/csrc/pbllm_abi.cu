@@ -245,6 +245,35 @@ int pbl_linear_forward_ws(const pbl_layer* layer, const void* x, int64_t ldx, vo
     return launch_gemv(L, x, ldx, y, ldy, M, (cudaStream_t)stream);
 }
 
+int pbl_linear_forward_push(const pbl_layer* layer, const void* x, int64_t ldx, const pbl_peer_push* push, int64_t ldy, int64_t M,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+    if (!layer || !push) { set_error("pbl_linear_forward_push: null layer / push"); return PBL_ERR_NULL; }
+    const Layer& L = *reinterpret_cast<const Layer*>(layer);
+    if (M <= 0 || M > 16) { set_error("pbl_linear_forward_push: M=%lld, one decode pass handles 1..16 tokens", (long long)M); return PBL_ERR_SHAPE; }
+    if (!x) { set_error("pbl_linear_forward_push: null x"); return PBL_ERR_NULL; }
+    if (push->n_ranks < 1 || push->n_ranks > PBL_MAX_PEERS || push->rank < 0 || push->rank >= push->n_ranks) {
+        set_error("pbl_linear_forward_push: bad rank %d of %d", push->rank, push->n_ranks); return PBL_ERR_SHAPE;
+    }
+    if (!push->sync_ctr) { set_error("pbl_linear_forward_push: null sync_ctr"); return PBL_ERR_NULL; }
+    for (int d = 0; d < push->n_ranks; ++d)
+        if (!push->y[d] || !push->flags[d]) { set_error("pbl_linear_forward_push: null y / flags pointer of rank %d", d); return PBL_ERR_NULL; }
+    if (ldx < L.K || ldy < L.N) { set_error("pbl_linear_forward_push: leading dimension too small"); return PBL_ERR_SHAPE; }
+    int rc = device_check_impl();
+    if (rc) return rc;
+    if (!decode_supported(L, ldx, M)) { set_error("pbl_linear_forward_push needs a block-stream (fp16 / bf16) layer"); return PBL_ERR_UNSUPPORTED; }
+    return launch_decode(L, x, ldx, nullptr, ldy, M, workspace, workspace_bytes, (cudaStream_t)stream, push);
+}
+
+int pbl_peer_wait(const pbl_peer_push* push, void* stream) {
+    if (!push || !push->sync_ctr) { set_error("pbl_peer_wait: null push"); return PBL_ERR_NULL; }
+    if (push->n_ranks < 1 || push->n_ranks > PBL_MAX_PEERS || push->rank < 0 || push->rank >= push->n_ranks || !push->flags[push->rank]) {
+        set_error("pbl_peer_wait: bad rank / flags"); return PBL_ERR_SHAPE;
+    }
+    int rc = device_check_impl();
+    if (rc) return rc;
+    return launch_peer_wait(*push, (cudaStream_t)stream);
+}
+
 int pbl_stream_layout(int64_t N, int64_t K, int64_t groupsize, int dtype, pbl_stream_sizes* out) {
     if (!out) { set_error("pbl_stream_layout: out is NULL"); return PBL_ERR_NULL; }
     if (dtype != PBL_F16 && dtype != PBL_BF16) { set_error("the block-stream layout holds fp16 / bf16 layers"); return PBL_ERR_DTYPE; }

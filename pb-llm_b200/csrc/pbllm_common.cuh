@@ -83,7 +83,8 @@ size_t decode_workspace_bytes(const Layer& L, int64_t M);
 void decode_set_trace(void* buf, size_t bytes);
 void decode_plan(int64_t N, int64_t K, int64_t M, int sms, int ctas_per_sm, uint32_t out[8]);
 int launch_decode(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws, size_t ws_bytes,
-                  cudaStream_t s);
+                  cudaStream_t s, const pbl_peer_push* push = nullptr);
+int launch_peer_wait(const pbl_peer_push& push, cudaStream_t s);
 size_t bireal_workspace_bytes(const Layer& L, int64_t M);
 size_t bireal_fixup_workspace_bytes(const Layer& L, int64_t M);
 int launch_bireal(const Layer& L, const void* x, int64_t ldx, int x_dtype, float* y, int64_t ldy, int64_t M, void* workspace,

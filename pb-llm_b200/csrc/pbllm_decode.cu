@@ -59,6 +59,15 @@ struct Params {
     uint32_t q, rem;      // blocks per warp: nblocks / (grid * 8) and the remainder (the first `rem` warps take one more)
     uint32_t has_mid;     // some (row, group) has lo != -hi: the mid * sum(x) term is needed
     unsigned long long* trace;   // kTrace builds only: [cta][warp][8] globaltimer stamps of this launch
+    // row-sharded execution (kPush): this rank's [M, N] slice is stored straight into the y of every rank of the node
+    // (peer-mapped pointers, already offset to the slice's first column), and the all-gather's completion is an in-kernel
+    // flag exchange: the last CTA of the grid publishes a new epoch in every rank's flag array, the next pushed kernel
+    // waits for all ranks' flags of the previous one before it touches its activations.
+    void* y_dst[PBL_MAX_PEERS];
+    uint32_t* flag_dst[PBL_MAX_PEERS];   // flag array (u32 [PBL_MAX_PEERS]) of every destination rank; we write entry [rank]
+    uint32_t* flag_local;                // this rank's own flag array
+    uint32_t* sync_ctr;                  // local: [0] = warps done (the last one resets it), [1] = epoch of the last push
+    uint32_t n_dst, rank, wait_prev;
 };
 }  // namespace dk
 
@@ -117,7 +126,16 @@ __device__ __forceinline__ unsigned long long dk_now() {
 // kNT = token groups of 8 per pass: 1 (M <= 8), or 2 (9..16 tokens against ONE expansion of each block; the second group
 // lives in its own variables).  kLean = the common case compiled without its branches: one group per row, activations
 // 32-byte aligned with K a multiple of 64 (the launcher checks).
-template <typename T, int kOcc, bool kTrace = false, int kNT = 1, bool kLean = false>
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* a) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* a, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a), "r"(v) : "memory");
+}
+
+template <typename T, int kOcc, bool kTrace = false, int kNT = 1, bool kLean = false, bool kPush = false>
 __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk::Params p) {
     using namespace dk;
     constexpr int kWarpBytes = dk::kWarpBytes + (kNT - 1) * kHeadBytes;
@@ -332,6 +350,15 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     if (kTrace) tr[1] = dk_now();
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (kTrace) tr[2] = dk_now();
+    if constexpr (kPush) {                              // the previous linear's slices from every rank have landed?
+        if (p.wait_prev) {
+            if (tid < p.n_dst) {
+                const uint32_t want = p.sync_ctr[1];    // epoch our own previous pushed kernel published
+                while ((int32_t)(ld_acquire_sys(p.flag_local + tid) - want) < 0) { }
+            }
+            __syncthreads();
+        }
+    }
     XF X0, X1;
     X0.a = X0.b = X0.a2 = X0.b2 = X1.a = X1.b = X1.a2 = X1.b2 = make_uint4(0, 0, 0, 0);
     if (w_lo < w_hi) load_x_next(X0);
@@ -414,8 +441,14 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
                     const float bv = p.bias ? p.bias[orow] : 0.f;
 #pragma unroll
                     for (int m = 0; m < kTokP; ++m)
-                        if (m0 + m < p.M)
-                            reinterpret_cast<T*>(p.y)[(int64_t)(m0 + m) * p.ldy + orow] = from_f32<T>(bv + tail_red[m * kRgRows + lane]);
+                        if (m0 + m < p.M) {
+                            const T v = from_f32<T>(bv + tail_red[m * kRgRows + lane]);
+                            if constexpr (kPush) {
+                                for (uint32_t d = 0; d < p.n_dst; ++d) reinterpret_cast<T*>(p.y_dst[d])[(int64_t)(m0 + m) * p.ldy + orow] = v;
+                            } else {
+                                reinterpret_cast<T*>(p.y)[(int64_t)(m0 + m) * p.ldy + orow] = v;
+                            }
+                        }
                 }
                 __syncwarp();
                 if (more) {                                      // the staging area is the tile: back to +1.0
@@ -451,7 +484,6 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     if (kTrace) tr[3] = dk_now();
     __syncthreads();
     if (kTrace) tr[4] = dk_now();
-    if (c_lo >= c_hi) return;
     auto trace_out = [&]() {
         if (kTrace && lane == 0) {
             tr[6] = dk_now();
@@ -462,10 +494,29 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
             for (int i = 0; i < 8; ++i) o[i] = tr[i];
         }
     };
+    // kPush: when every warp that stores outputs (warps 0 and 1 of every CTA, below; the loop's stores are ordered before
+    // them by the barrier above) has passed its system-scope fence, the last one publishes the new epoch to every rank.
+    auto publish = [&]() {
+        if constexpr (kPush) {
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_system();
+                const uint32_t total = 2u * gridDim.x * gridDim.y;
+                if (atomicAdd(p.sync_ctr, 1u) == total - 1u) {
+                    p.sync_ctr[0] = 0u;
+                    const uint32_t epoch = p.sync_ctr[1] + 1u;
+                    p.sync_ctr[1] = epoch;
+                    __threadfence_system();
+                    for (uint32_t d = 0; d < p.n_dst; ++d) st_release_sys(p.flag_dst[d] + p.rank, epoch);
+                }
+            }
+        }
+    };
     // Two warps finish the CTA: thread t < 64 owns four consecutive outputs per token group -- token 8u + (t>>3), rows
     // 4*(t&7)..+3 of the row group, i.e. float4 number 64u + t of every [token][row] partial buffer -- so each partial costs
     // one LDS.128 per thread and group.
     if (tid >= 64u) { if (kTrace) tr[5] = tr[4]; trace_out(); return; }
+    if (c_lo >= c_hi) { publish(); return; }
     const uint32_t rg_a = s_meta[0], rg_b = s_meta[1];
     const uint32_t om = tid >> 3, or4 = (tid & 7u) * 4u;
     uint32_t hrg[kWarps], trg[kWarps];
@@ -474,7 +525,7 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     const bool hs = s_meta[2] != 0u, ts = s_meta[5] != 0u;
 #pragma unroll
     for (int u = 0; u < kNT; ++u) {                          // one round per token group: float4 number 64u + t of the buffers
-        T* yout = reinterpret_cast<T*>(p.y) + (int64_t)(m0 + kTok * u + om) * p.ldy;
+        const int64_t yoff = (int64_t)(m0 + kTok * u + om) * p.ldy;
         const bool tok_ok = (m0 + kTok * u + (int)om) < p.M;
         auto emit = [&](uint32_t r, const float4 v) {            // + bias, round, store the four outputs of row group r
             const int orow = (int)(r * kRgRows + or4);
@@ -482,7 +533,14 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
             if (tok_ok) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (orow + j < p.N) yout[orow + j] = from_f32<T>((p.bias ? p.bias[orow + j] : 0.f) + vv[j]);
+                    if (orow + j < p.N) {
+                        const T o = from_f32<T>((p.bias ? p.bias[orow + j] : 0.f) + vv[j]);
+                        if constexpr (kPush) {
+                            for (uint32_t d = 0; d < p.n_dst; ++d) (reinterpret_cast<T*>(p.y_dst[d]) + yoff)[orow + j] = o;
+                        } else {
+                            (reinterpret_cast<T*>(p.y) + yoff)[orow + j] = o;
+                        }
+                    }
             }
         };
         float4 v_split[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};   // head / tail row group (when shared)
@@ -545,6 +603,7 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
             }
         }
     }
+    publish();
     trace_out();
 }
 
@@ -638,8 +697,9 @@ size_t decode_workspace_bytes(const Layer& L, int64_t M) {
     return decode_geom(L, M).ws_bytes;
 }
 
-template <typename T, int kOcc, int kNT, bool kLean>
-static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws, cudaStream_t s) {
+template <typename T, int kOcc, int kNT, bool kLean, bool kPush = false>
+static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws, cudaStream_t s,
+                           const pbl_peer_push* push = nullptr) {
     const DecodeGeom g = decode_geom(L, M);
     const int smem = dk::kWarps * (dk::kWarpBytes + (kNT - 1) * dk::kHeadBytes);
     static int attr_smem_dev[64] = {};   // function attributes are per device
@@ -647,7 +707,7 @@ static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, 
     cudaGetDevice(&cur_dev);
     if (cur_dev < 0 || cur_dev >= 64) cur_dev = 0;
     if (attr_smem_dev[cur_dev] < smem) {
-        int rc = check_cuda(cudaFuncSetAttribute(decode_mma_kernel<T, kOcc, false, kNT, kLean>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+        int rc = check_cuda(cudaFuncSetAttribute(decode_mma_kernel<T, kOcc, false, kNT, kLean, kPush>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                             "cudaFuncSetAttribute(decode smem)");
         if (rc) return rc;
         attr_smem_dev[cur_dev] = smem;
@@ -660,6 +720,13 @@ static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, 
     p.M = (int)M; p.N = (int)L.N; p.K = (int)L.K;
     p.tiles_c = (uint32_t)L.tiles_c; p.groups = (uint32_t)L.groups; p.tiles_per_group = (uint32_t)L.tiles_per_group;
     p.nblocks = g.nblocks; p.rgs = g.rgs; p.slots = g.slots; p.q = g.q; p.rem = g.rem;
+    p.n_dst = 0; p.rank = 0; p.wait_prev = 0; p.flag_local = nullptr; p.sync_ctr = nullptr;
+    for (int d = 0; d < PBL_MAX_PEERS; ++d) { p.y_dst[d] = nullptr; p.flag_dst[d] = nullptr; }
+    if (kPush) {
+        p.n_dst = (uint32_t)push->n_ranks; p.rank = (uint32_t)push->rank; p.wait_prev = push->wait_prev ? 1u : 0u;
+        p.flag_local = push->flags[push->rank]; p.sync_ctr = push->sync_ctr;
+        for (int d = 0; d < push->n_ranks; ++d) { p.y_dst[d] = push->y[d]; p.flag_dst[d] = push->flags[d]; }
+    }
 
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(g.grid, g.passes);
@@ -674,14 +741,14 @@ static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, 
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     cudaError_t le;
-    if (g_trace && g_trace_next < g_trace_launches && kOcc == 2 && kNT == 1 && !kLean) {
+    if (g_trace && g_trace_next < g_trace_launches && kOcc == 2 && kNT == 1 && !kLean && !kPush) {
         p.trace = g_trace + (g_trace_next++) * kTraceStride;
         static bool tattr = false;
         if (!tattr) { cudaFuncSetAttribute(decode_mma_kernel<T, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); tattr = true; }
         le = cudaLaunchKernelEx(&cfg, decode_mma_kernel<T, 2, true>, p);
     } else {
         p.trace = nullptr;
-        le = cudaLaunchKernelEx(&cfg, decode_mma_kernel<T, kOcc, false, kNT, kLean>, p);
+        le = cudaLaunchKernelEx(&cfg, decode_mma_kernel<T, kOcc, false, kNT, kLean, kPush>, p);
     }
     count_launch();
     return check_cuda(le, "decode launch");
@@ -689,8 +756,22 @@ static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, 
 
 // ws == nullptr: take a transient workspace from the stream-ordered pool and zero it (slower: the memset
 // sits between consecutive decode kernels); callers on the hot path pass a persistent zero-initialised workspace.
+__global__ void peer_wait_kernel(const uint32_t* __restrict__ flag_local, const uint32_t* __restrict__ sync_ctr, uint32_t n) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x < n) {
+        const uint32_t want = sync_ctr[1];
+        while ((int32_t)(ld_acquire_sys(flag_local + threadIdx.x) - want) < 0) { }
+    }
+}
+
+int launch_peer_wait(const pbl_peer_push& push, cudaStream_t s) {
+    peer_wait_kernel<<<1, 32, 0, s>>>(push.flags[push.rank], push.sync_ctr, (uint32_t)push.n_ranks);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "peer_wait launch");
+}
+
 int launch_decode(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws, size_t ws_bytes,
-                  cudaStream_t s) {
+                  cudaStream_t s, const pbl_peer_push* push) {
     const DecodeGeom g = decode_geom(L, M);
     void* own = nullptr;
     if (ws) {
@@ -712,10 +793,21 @@ int launch_decode(const Layer& L, const void* x, int64_t ldx, void* y, int64_t l
                      : launch_decode_t<__nv_bfloat16, OCC, NT, true>(L, x, ldx, y, ldy, M, ws, s))                             \
               : (f16 ? launch_decode_t<__half, OCC, NT, false>(L, x, ldx, y, ldy, M, ws, s)                                    \
                      : launch_decode_t<__nv_bfloat16, OCC, NT, false>(L, x, ldx, y, ldy, M, ws, s))
-    if (g.nt == 2) { PBL_DK_LAUNCH(2, 2); }              // 9..16 tokens in one pass
+#define PBL_DK_PUSH(NT)                                                                                                        \
+    rc = lean ? (f16 ? launch_decode_t<__half, 2, NT, true, true>(L, x, ldx, y, ldy, M, ws, s, push)                           \
+                     : launch_decode_t<__nv_bfloat16, 2, NT, true, true>(L, x, ldx, y, ldy, M, ws, s, push))                   \
+              : (f16 ? launch_decode_t<__half, 2, NT, false, true>(L, x, ldx, y, ldy, M, ws, s, push)                          \
+                     : launch_decode_t<__nv_bfloat16, 2, NT, false, true>(L, x, ldx, y, ldy, M, ws, s, push))
+    if (push) {
+        if (g.passes != 1) { set_error("pbl_linear_forward_push: one decode pass only (M <= 16)"); rc = PBL_ERR_UNSUPPORTED; }
+        else if (g.nt == 2) { PBL_DK_PUSH(2); }
+        else { PBL_DK_PUSH(1); }
+    }
+    else if (g.nt == 2) { PBL_DK_LAUNCH(2, 2); }         // 9..16 tokens in one pass
     else if (dk_occupancy() == 3) { PBL_DK_LAUNCH(3, 1); }
     else { PBL_DK_LAUNCH(2, 1); }
 #undef PBL_DK_LAUNCH
+#undef PBL_DK_PUSH
     if (own) {
         const int rf = check_cuda(cudaFreeAsync(own, s), "cudaFreeAsync(decode workspace)");
         if (!rc) rc = rf;
