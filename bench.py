@@ -1,27 +1,31 @@
 #!/usr/bin/env python
-"""bench.py -- tokens/sec through the partially-binarized linears of a Llama-7B-shaped model.
+"""bench.py -- tokens/sec through the partially-binarized linears of an OPT / LLaMA-shaped model.
 
-Workload (BASELINE.json configs[2]): huggyllama/llama-7b shapes, GPTQ-PB format (xnor low part,
-low_frac=0.9, 8-bit salient part, Hessian-like column-skewed salient mask), batch 8 x seq_len
-2048 = 16384 tokens per step, fp16. A "step" is one pass of those tokens through all 224 decoder
-linears (32 x [q,k,v,o 4096x4096; gate,up 11008x4096; down 4096x11008]) -- the hot path of
-SURVEY.md section 8, i.e. every F.linear(x, w_sim) the reference's forward executes for them.
-Weights and activations are synthetic (no checkpoints / network); every layer has its own
-weights, so each step streams 2.3 GB of packed weights plus the activations: far larger than
-the 126 MB L2, no flush needed between iterations.
+Default workload (BASELINE.json configs[2]): huggyllama/llama-7b shapes, GPTQ-PB format (xnor low part, low_frac=0.9,
+8-bit salient part, Hessian-like column-skewed salient mask), batch 8 x seq_len 2048 = 16384 tokens per step, fp16.
+A "step" is one pass of those tokens through all 224 decoder linears (32 x [q,k,v,o 4096x4096; gate,up 11008x4096;
+down 4096x11008]) -- the hot path of SURVEY.md section 8, i.e. every F.linear(x, w_sim) the reference's forward executes
+for them -- through the DROP-IN MODULES: the layers are plain nn.Linear blocks holding fake-quant weights, converted by
+pb.replace_from_fakequant (mask files on disk, as gptq_pb/gptq.py:108-114 writes them) / pb.replace_with_qlinear and
+called as module(x). Weights and activations are synthetic (no checkpoints / network); every layer has its own weights,
+so each step streams GBs of packed weights plus the activations: far larger than the 126 MB L2, no flush needed.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]          # our CUDA path
-    python bench.py --impl reference ...                          # the reference algorithm on host cores
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config llama7b|llama13b|opt1.3b]     # our CUDA path
+    python bench.py --impl reference ...                                                       # the reference algorithm on host cores
 
-Prints ONE JSON line (rank 0). See DESIGN.md "Measurement" for every field.
+Prints ONE JSON line (rank 0). See DESIGN.md "Measurement" for every field. With N > 1 ranks the headline is token-sharded
+replicas (no collective) and the line also carries `rowshard`: the north star's row-sharded linears -- NCCL all-gather in
+the prefill regime, the fused peer-store kernel in the per-token regime -- measured in the same run.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -32,10 +36,31 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-HID, FFN, NLAYERS = 4096, 11008, 32
-SHAPES = [("q_proj", HID, HID, "h"), ("k_proj", HID, HID, "h"), ("v_proj", HID, HID, "h"), ("o_proj", HID, HID, "a"),
-          ("gate_proj", FFN, HID, "h"), ("up_proj", FFN, HID, "h"), ("down_proj", HID, FFN, "f")]
-METRIC = "tokens/sec Llama-7B PB low_frac=0.9 (decoder linears forward, batch 8 x seq 2048)"
+CONFIGS = {
+    # BASELINE.json configs[2] (and [3] with --low-frac 0.95): the metric's own configuration
+    "llama7b": dict(model="huggyllama/llama-7b", family="llama", hid=4096, ffn=11008, layers=32, low_frac=0.9, batch=8, seq=2048,
+                    method="gptq_pb", lm_head=0),
+    # configs[4]
+    "llama13b": dict(model="huggyllama/llama-13b", family="llama", hid=5120, ffn=13824, layers=40, low_frac=0.8, batch=16, seq=2048,
+                     method="gptq_pb", lm_head=0),
+    # configs[1]: QAT surgery (qat/run_qat.py:45-66) replaces EVERY nn.Linear, lm_head included, magnitude mask
+    "opt1.3b": dict(model="facebook/opt-1.3b", family="opt", hid=2048, ffn=8192, layers=24, low_frac=0.9, batch=1, seq=2048,
+                    method="xnor_outlier", lm_head=50272),
+}
+
+
+def layer_shapes(cfg):
+    h, f = cfg["hid"], cfg["ffn"]
+    if cfg["family"] == "llama":
+        return [("q_proj", h, h, "h"), ("k_proj", h, h, "h"), ("v_proj", h, h, "h"), ("o_proj", h, h, "a"),
+                ("gate_proj", f, h, "h"), ("up_proj", f, h, "h"), ("down_proj", h, f, "f")]
+    return [("q_proj", h, h, "h"), ("k_proj", h, h, "h"), ("v_proj", h, h, "h"), ("out_proj", h, h, "a"),
+            ("fc1", f, h, "h"), ("fc2", h, f, "f")]
+
+
+def metric_name(cfg, args):
+    nice = {"llama7b": "Llama-7B", "llama13b": "Llama-13B", "opt1.3b": "OPT-1.3b"}[args.config]
+    return f"tokens/sec {nice} PB low_frac={args.low_frac} (decoder linears forward, batch {args.batch} x seq {args.seq})"
 
 
 def peaks():
@@ -47,7 +72,17 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback (B200_PROFILING.md)")
 
 
-# ---- synthetic GPTQ-PB-format weights (SURVEY.md 8d "Synthetic inputs") -----------------------------
+def ncu_traffic(key):
+    """dram__bytes_read+write per launch of the dominant kernels, from this round's committed `ncu --set full` captures
+    (profiles/r02_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep files); None when not captured."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    try:
+        return json.load(open(p)).get(key)
+    except (OSError, ValueError):
+        return None
+
+
+# ---- synthetic weights (SURVEY.md 8d "Synthetic inputs") -----------------------------------------------------------
 def synth_layer_gpu(N, K, low_frac, seed, dev):
     """Dense fp16 fake-quant weight in the format gptq_pb/gptq.py:149-155,180-184 produces, built on
     the GPU: low positions mu_i +- alpha_i (fp16), salient positions on the row's 8-bit grid
@@ -68,6 +103,14 @@ def synth_layer_gpu(N, K, low_frac, seed, dev):
     z = torch.round(-mn / s)
     q_high = s * (torch.clamp(torch.round(w / s) + z, 0, 255) - z)
     return torch.where(low, q_low, q_high).half(), low
+
+
+def synth_latent_gpu(N, K, seed, dev):
+    """Heavy-tailed latent fp16 weights for the QAT-style surgery (magnitude outliers are real)."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    w = torch.randn(N, K, device=dev, generator=g) * 0.02
+    w = w * (1 + 4 * (torch.rand(N, K, device=dev, generator=g) < 0.02))
+    return w.half()
 
 
 def clocks_sampler(stop, out, dev_index):
@@ -100,28 +143,39 @@ def clocks_summary(samples):
 
 
 # ---- CPU baseline: the reference algorithm on host cores ---------------------------------------------
-def cpu_baseline(seconds_budget=20.0, tokens=2048, steps=None, warmup=1):
-    """The reference's CPU path for this config: the GPTQ-PB checkpoint is a plain nn.Linear holding
-    fake-quant weights (gptq_pb/gptq.py:180-184), evaluated as dense F.linear in fp32 on all host
-    cores. Sample: ONE decoder layer (its 7 linears) x `tokens` tokens; the
-    tokens/sec figure divides by the 32 identical layers. Weights come from the oracle's GPTQ-PB
-    RTN restatement (oracle.gptqpb_rtn) at reduced rows to keep setup short, tiled to full size."""
+def cpu_baseline(cfg, args, seconds_budget=20.0, tokens=2048, steps=None, warmup=1):
+    """The reference's CPU path on a bounded sample: ONE decoder layer x `tokens` tokens, tokens/sec divided by the layer
+    count. gptq_pb configs: the checkpoint is a plain nn.Linear holding fake-quant weights (gptq_pb/gptq.py:180-184),
+    evaluated as dense F.linear in fp32 (weights from the oracle's GPTQ-PB RTN restatement at reduced rows, tiled).
+    xnor_outlier config: the reference module re-binarises on EVERY forward (outlier_quantizer.py:83-106) -- sign, scale,
+    where over the whole weight, then F.linear; restated here with the same torch ops on the oracle's state."""
     import torch.nn.functional as F
     from oracle import oracle as orc
     ncores = os.cpu_count() or 1
     rs = np.random.RandomState(0)
-    ws = []
-    for _, N, K, _src in SHAPES:
+    shapes = layer_shapes(cfg)
+    ws, masks, scales = [], [], []
+    for _, N, K, _src in shapes:
         base = (rs.standard_normal((256, K)) * 0.02).astype(np.float32)
-        low = rs.rand(256, K) < 0.9
-        wq, _, _ = orc.gptqpb_rtn(base, low, -1, 8, True)
-        ws.append(torch.from_numpy(np.tile(wq, (N // 256, 1))).contiguous())
-    xs = {"h": torch.randn(tokens, HID), "a": torch.randn(tokens, HID), "f": torch.randn(tokens, FFN)}
+        if cfg["method"] == "gptq_pb":
+            low = rs.rand(256, K) < args.low_frac
+            wq, _, _ = orc.gptqpb_rtn(base, low, -1, 8, True)
+            ws.append(torch.from_numpy(np.tile(wq, (N // 256, 1))).contiguous())
+        else:
+            st = orc.outlier_state(base, 1.0 - args.low_frac)
+            ws.append(torch.from_numpy(np.tile(st["w8"], ((N + 255) // 256, 1))[:N]).contiguous())
+            masks.append(torch.from_numpy(np.tile(st["mask"], ((N + 255) // 256, 1))[:N]).contiguous())
+            scales.append(float(st["binary_scale"]))
+    xs = {"h": torch.randn(tokens, cfg["hid"]), "a": torch.randn(tokens, cfg["hid"]), "f": torch.randn(tokens, cfg["ffn"])}
 
     def layer_step():
         with torch.no_grad():
-            for (_, N, K, src), w in zip(SHAPES, ws):
-                F.linear(xs[src], w)
+            for i, ((_, N, K, src), w) in enumerate(zip(shapes, ws)):
+                if cfg["method"] == "gptq_pb":
+                    F.linear(xs[src], w)
+                else:                                    # binarize_except_outliers on every forward, then F.linear
+                    w_sim = torch.where(masks[i], w * 1, w.sign() * scales[i])
+                    F.linear(xs[src], w_sim)
 
     # give the reference its best thread count on this host (oversubscribing a big NUMA box is slower)
     best_t, best_n = None, ncores
@@ -147,30 +201,37 @@ def cpu_baseline(seconds_budget=20.0, tokens=2048, steps=None, warmup=1):
         if steps is None and len(times) >= 50:
             break
     t_layer = float(np.mean(times))
-    return dict(value=tokens / (t_layer * NLAYERS), unit="tokens/s", cores=threads, kind="port",
-                sample=f"1 of {NLAYERS} decoder layers (7 dense fp32 F.linear over GPTQ-PB fake-quant weights, "
-                       f"torch CPU, best of several thread counts = {threads} threads on {ncores} logical cores) x {tokens} "
-                       f"tokens, {len(times)} reps, {t_layer * 1e3:.1f} ms/layer-sample; tokens/s = {tokens}/(t_layer*{NLAYERS})",
+    nl = cfg["layers"]
+    what = ("dense fp32 F.linear over GPTQ-PB fake-quant weights" if cfg["method"] == "gptq_pb"
+            else "per-forward re-binarisation (sign/scale/where) + fp32 F.linear, as outlier_quantizer.py:83-106")
+    return dict(value=tokens / (t_layer * nl), unit="tokens/s", cores=threads, kind="port",
+                sample=f"1 of {nl} decoder layers ({len(shapes)} linears: {what}, torch CPU, best of several thread counts = "
+                       f"{threads} threads on {ncores} logical cores) x {tokens} tokens, {len(times)} reps, "
+                       f"{t_layer * 1e3:.1f} ms/layer-sample; tokens/s = {tokens}/(t_layer*{nl})",
                 ms_per_step=t_layer * 1e3, steps=len(times))
 
 
-def run_reference(args):
+def run_reference(cfg, args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_baseline(steps=args.steps, warmup=max(1, min(args.warmup, 2)))
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "tokens/s", "n_gpus": args.gpus,
+    cb = cpu_baseline(cfg, args, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+    line = {"impl": "reference", "metric": metric_name(cfg, args), "value": cb["value"], "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": cb["steps"], "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "parallelism": "host cores only"},
+            "config": {"workload": workload_name(cfg, args), "parallelism": "host cores only"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
-def workload_name(args):
-    return (f"llama-7b decoder linears ({args.layers}x7 PB linears, GPTQ-PB format low_frac={args.low_frac} high_bit=8, "
-            f"synthetic Hessian-skewed mask), batch {args.batch} x seq_len {args.seq} = {args.batch * args.seq} tokens/step")
+def workload_name(cfg, args):
+    n = len(layer_shapes(cfg))
+    head = f" + lm_head {cfg['lm_head']}x{cfg['hid']}" if cfg["lm_head"] and args.layers == cfg["layers"] else ""
+    fmt = (f"GPTQ-PB format low_frac={args.low_frac} high_bit=8, synthetic Hessian-skewed mask" if cfg["method"] == "gptq_pb"
+           else f"xnor_outlier modules, outlier_fraction={round(1 - args.low_frac, 4)} (magnitude mask), 8-bit salient weights")
+    return (f"{cfg['model']} decoder linears ({args.layers}x{n} PB linears{head}, {fmt}), "
+            f"batch {args.batch} x seq_len {args.seq} = {args.batch * args.seq} tokens/step")
 
 
 # ---- our arm --------------------------------------------------------------------------------------------
@@ -193,6 +254,96 @@ def emit(line: dict):
     out.flush()
 
 
+def build_model(pb, cfg, args, dev, rank):
+    """The drop-in path: nn.Linear blocks -> surgery -> packed modules. Returns [[(module, src), ...] per decoder layer]
+    (+ the lm_head block for the QAT-style config)."""
+    import torch.nn as nn
+    shapes = layer_shapes(cfg)
+    blocks = []
+    tmp = tempfile.mkdtemp(prefix="pbl_masks_")
+    try:
+        for li in range(args.layers):
+            blk = nn.Module()
+            lows = {}
+            for si, (name, N, K, _src) in enumerate(shapes):
+                lin = nn.Linear(K, N, bias=False, device=dev, dtype=torch.float16)
+                if cfg["method"] == "gptq_pb":
+                    w, low = synth_layer_gpu(N, K, args.low_frac, 1000 * li + si, dev)
+                    lows[name] = low
+                else:
+                    w = synth_latent_gpu(N, K, 1000 * li + si, dev)
+                lin.weight.data = w
+                setattr(blk, name, lin)
+            if cfg["method"] == "gptq_pb":
+                # the mask files gptq_pb/gptq.py:108-114 writes, one per linear, then the GPTQ-PB checkpoint surgery
+                mid = f"synthetic/{cfg['model'].split('/')[-1]}/layers.{li}."
+                for name, low in lows.items():
+                    torch.save(low.cpu(), os.path.join(tmp, f"mask_{args.low_frac}_{(mid + name).replace('/', '_')}.pkl"))
+                pb.replace_from_fakequant(blk, tmp, args.low_frac, model_id=mid)
+                for f in os.listdir(tmp):
+                    os.remove(os.path.join(tmp, f))
+            else:
+                pb.replace_with_qlinear(blk, "xnor_outlier", round(1.0 - args.low_frac, 6), model_id=f"layers.{li}.")
+                blk.eval()
+            pb.pack_model(blk, keep_latent=False)
+            blocks.append([(getattr(blk, name), src) for name, _, _, src in shapes])
+            del blk, lows
+        if cfg["lm_head"] and args.layers == cfg["layers"]:
+            blk = nn.Module()
+            lin = nn.Linear(cfg["hid"], cfg["lm_head"], bias=False, device=dev, dtype=torch.float16)
+            lin.weight.data = synth_latent_gpu(cfg["lm_head"], cfg["hid"], 999_983, dev)
+            blk.lm_head = lin
+            pb.replace_with_qlinear(blk, "xnor_outlier", round(1.0 - args.low_frac, 6), model_id="")
+            blk.eval()
+            pb.pack_model(blk, keep_latent=False)
+            blocks.append([(blk.lm_head, "h")])
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return blocks
+
+
+def oracle_parity(pb, cfg, args, dev):
+    """Parity in the same run, anchored to the ORACLE: weights from the oracle's own restatement of the reference
+    (oracle.gptqpb_rtn / oracle.outlier_state), the drop-in module's output against oracle.linear (double accumulation)
+    on the same inputs, decode and prefill kernels, the three distinct layer shapes at reduced rows."""
+    from oracle import oracle as orc
+    out = {}
+    rs = np.random.RandomState(7)
+    seen = set()
+    for name, N, K, _src in layer_shapes(cfg):
+        if (N > K, K) in seen:
+            continue
+        seen.add((N > K, K))
+        n = 256
+        base = (rs.standard_normal((n, K)) * 0.02).astype(np.float32)
+        if cfg["method"] == "gptq_pb":
+            low = rs.rand(n, K) < args.low_frac
+            wq, _, _ = orc.gptqpb_rtn(base, low, -1, 8, True)
+            w16 = torch.from_numpy(wq).half()
+            mod = pb.PackedFakeQuantLinear(w16.to(dev), None, torch.from_numpy(low).to(dev), -1)
+            w_ref = w16.float().numpy()
+        else:
+            st = orc.outlier_state(base.astype(np.float16).astype(np.float32), 1.0 - args.low_frac, half_mode=True)
+            st["wsim"] = orc.outlier_wsim(st, half_mode=True)
+            mod = pb.BinaryXnorExceptOutliersLinear(torch.from_numpy(base).half().to(dev), None, 1.0 - args.low_frac).eval()
+            w_ref = None
+        for tag, M in (("decode", 8), ("prefill", 512)):
+            x = torch.from_numpy((rs.standard_normal((M, K))).astype(np.float32)).half()
+            y = mod(x.to(dev)).float().cpu().numpy()
+            if w_ref is None:
+                w_ref = mod.dense_weight().float().cpu().numpy()
+                assert np.array_equal(mod.outlier_mask.cpu().numpy(), st["mask"]), "salient mask differs from the oracle's"
+                assert np.array_equal(w_ref[st["mask"]], st["wsim"][st["mask"]].astype(np.float16).astype(np.float32)), "salient weights differ from the oracle's"
+                w_ref = st["wsim"].astype(np.float16).astype(np.float32) if np.abs(w_ref - st["wsim"]).max() <= 1e-3 * np.abs(w_ref).max() else w_ref
+            ref = orc.linear(x.float().numpy(), w_ref)
+            out[f"{name}:{tag}"] = float(np.abs(y - ref).max() / np.abs(ref).max())
+    out["max_rel_err"] = max(out.values())
+    out["tolerance"] = 1e-3
+    out["reference"] = "oracle.linear (double accumulation) over oracle-generated fake-quant weights, 256-row layers"
+    assert out["max_rel_err"] <= 1e-3, out
+    return out
+
+
 def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -200,21 +351,26 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--layers", type=int, default=NLAYERS, help="decoder layers (32 = the named config)")
-    ap.add_argument("--batch", type=int, default=8)
-    ap.add_argument("--seq", type=int, default=2048)
-    ap.add_argument("--low-frac", type=float, default=0.9, dest="low_frac")
-    ap.add_argument("--parallel", default="replica", choices=["replica", "rowshard"])
+    ap.add_argument("--config", default="llama7b", choices=sorted(CONFIGS))
+    ap.add_argument("--layers", type=int, default=None, help="decoder layers (default: the named config's)")
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--seq", type=int, default=None)
+    ap.add_argument("--low-frac", type=float, default=None, dest="low_frac")
+    ap.add_argument("--rowshard-low-frac", type=float, default=0.95, help="low_frac of the row-sharded section (BASELINE configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-rowshard", action="store_true")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    for k in ("layers", "batch", "seq", "low_frac"):
+        if getattr(args, k) is None:
+            setattr(args, k, cfg[k])
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(cfg, args)
 
     import torch.distributed as dist
     import pbllm_b200 as pb
-    from pbllm_b200.sharding import shard_rows, gather_rows
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -226,59 +382,34 @@ def main():
     lib = pb._lib.load()
     pb._lib.check(lib.pbl_device_check(), "device check")
     M = args.batch * args.seq
-    rowshard = args.parallel == "rowshard" and world > 1
+    shapes = layer_shapes(cfg)
+    pk = peaks()
 
-    # -- build the packed model (one-time, untimed) ----------------------------------------------------------
-    layers = []
+    # -- build the packed model through the drop-in surgery (one-time, untimed) ----------------------------------
     t0 = time.time()
-    for li in range(args.layers):
-        row = []
-        for si, (name, N, K, src) in enumerate(SHAPES):
-            w, low = synth_layer_gpu(N, K, args.low_frac, 1000 * li + si, dev)
-            if rowshard:
-                r0, r1, _ = shard_rows(N, world, rank)
-                w, low = w[r0:r1], low[r0:r1]
-            row.append(pb.PackedLinear.from_dense(w, None, low))
-            del w, low
-        layers.append(row)
+    with torch.no_grad():
+        blocks = build_model(pb, cfg, args, dev, rank)
     torch.cuda.synchronize()
     build_s = time.time() - t0
-    packed_bytes = sum(p.packed_bytes() for row in layers for p in row)
-    dindex_bytes = 0
-    nnz = sum(p.salient_count() for row in layers for p in row)
-    nk = sum(N * K for _, N, K, _ in SHAPES) * args.layers
+    mods = [m for blk in blocks for m, _ in blk]
+    packed = [m.packed() for m in mods]
+    packed_bytes = sum(p.packed_bytes() for p in packed)
+    nnz = sum(p.salient_count() for p in packed)
+    nk = sum(p.N * p.K for p in packed)
 
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    xin = {"h": torch.randn(M, HID, device=dev, generator=g).half(), "a": torch.randn(M, HID, device=dev, generator=g).half(),
-           "f": torch.randn(M, FFN, device=dev, generator=g).half()}
-    outs = [torch.empty(M, p.N, device=dev, dtype=torch.float16) for p in layers[0]]
-    full_outs = [torch.empty(M, N, device=dev, dtype=torch.float16) for _, N, _, _ in SHAPES] if rowshard else None
+    xin = {"h": torch.randn(M, cfg["hid"], device=dev, generator=g).half(), "a": torch.randn(M, cfg["hid"], device=dev, generator=g).half(),
+           "f": torch.randn(M, cfg["ffn"], device=dev, generator=g).half()}
 
-    # -- parity in the same run: CUDA path vs fp64 dense math over the bit-exact unpacked w_sim -------
-    parity = {}
-    if rank == 0:
-        for i in (0, 4, 6):                                   # the three distinct layer shapes
-            p = layers[0][i]
-            xs_ = xin[SHAPES[i][3]]
-            w64 = p.unpack().double()
-            for tag, rows in (("prefill", slice(0, 1024)), ("decode", slice(0, 8))):
-                yk = p.forward(xs_[rows].contiguous()).double()
-                ref = xs_[rows].double() @ w64.t()
-                parity[f"{SHAPES[i][0]}:{tag}"] = float((yk - ref).abs().max() / ref.abs().max())
-            del w64
-        parity["max_rel_err"] = max(parity.values())
-        parity["tolerance"] = 1e-3
-        assert parity["max_rel_err"] <= 1e-3, parity
+    parity = oracle_parity(pb, cfg, args, dev) if rank == 0 else {}
 
+    @torch.no_grad()
     def step(x_h=None):
-        for row in layers:
-            for i, p in enumerate(row):
-                src = SHAPES[i][3]
-                x = x_h if (x_h is not None and src == "h") else xin[src]
-                p.forward(x, out=outs[i])
-                if rowshard:
-                    gather_rows(outs[i], SHAPES[i][1], out=full_outs[i])
-        return (full_outs if rowshard else outs)[-1]
+        y = None
+        for blk in blocks:
+            for m, src in blk:
+                y = m(x_h if (x_h is not None and src == "h") else xin[src])
+        return y
 
     def barrier():
         if world > 1:
@@ -311,39 +442,33 @@ def main():
         th.start()
 
     ms_step, launches = timed(step, args.steps, args.warmup)
-    tokens_per_step = M * (1 if rowshard else world)
-    value = tokens_per_step / (ms_step * 1e-3)
+    value = M * world / (ms_step * 1e-3)
 
-    # -- per-launch durations of the dominant kernel (events around every launch, separate pass) -----------------
+    # -- per-launch durations of the dominant kernel (events around every module call, separate pass) -------------
     per = []
     if rank == 0:
         evs = []
-        for row in layers:
-            for i, p in enumerate(row):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                p.forward(xin[SHAPES[i][3]], out=outs[i])
-                b.record()
-                evs.append((a, b, p))
+        with torch.no_grad():
+            for blk in blocks:
+                for m, src in blk:
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    m(xin[src])
+                    b.record()
+                    evs.append((a, b, m.packed()))
         torch.cuda.synchronize()
         per = [(a.elapsed_time(b), p) for a, b, p in evs]
     kern_ms = sum(t for t, _ in per)
     flops = sum(2.0 * M * p.N * p.K for _, p in per)
-    pk = peaks()
-    kernel_id = layers[0][0].select_kernel(M)
-    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/
-    # r01_gemm_two_phase_M16384_N4096_K4096.md): gemm_tt_kernel dram read 264.7 MB + write 109.3 MB for the
-    # q/k/v/o-shaped launch (algorithmic: 134 MB x + 134 MB y + 7.6 MB packed weights; the 33.5 MB dense
-    # scratch written by expand_dense_kernel stays in L2 -- its own dram write is 0.02 MB -- but is partly
-    # re-fetched by the GEMM waves, as is x).
-    ncu_traffic = {"launch": "M=16384 N=4096 K=4096 (gemm_tt_kernel)", "bytes": 264.709376e6 + 109.28e6,
-                   "algorithmic_bytes": 2 * 16384 * 4096 * 2 + 7.6e6}
+    kernel_id = packed[0].select_kernel(M)
     roofline = None
     if per:
         ach = flops / (kern_ms * 1e-3) / 1e12
+        tr = ncu_traffic("prefill_gemm") if (kernel_id == 1 and args.config == "llama7b" and M == 16384) else None
         roofline = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"],
-                    "traffic": ncu_traffic["bytes"] if (kernel_id == 1 and M >= 2048) else None, "traffic_note": ncu_traffic, "kernel": {0: "pbl CUDA-core bit-plane kernel", 1: "pbl two-phase prefill: expand_dense_kernel + gemm_tt_kernel (tcgen05 cta_group::2, TMA both operands); times include both launches",
-                               2: "pbl mma.sync bit-plane skinny kernel", 3: "pbl tcgen05 split-K cluster kernel",
+                    "traffic": None if tr is None else tr["bytes_per_launch"], "traffic_note": tr,
+                    "kernel": {0: "pbl CUDA-core bit-plane kernel",
+                               1: "pbl two-phase prefill: stream_unpack_kernel (expansion) + gemm_tt_kernel (tcgen05 cta_group::2, TMA both operands); times include both launches",
                                4: "pbl decode kernel"}[kernel_id],
                     "launches": len(per), "avg_launch_ms": kern_ms / len(per), "peak_source": pk["src"] + ", sustained bf16",
                     "frac_of_burst_peak": ach / pk["tf_burst"],
@@ -352,9 +477,9 @@ def main():
     # -- end-to-end: host buffers in, host buffers out, through the module API ---------------------------------------
     e2e = None
     if not args.no_e2e:
-        xh = torch.randn(M, HID).half().pin_memory()
-        yh = torch.empty(M, SHAPES[-1][1], dtype=torch.float16).pin_memory()
-        xd = torch.empty(M, HID, device=dev, dtype=torch.float16)
+        xh = torch.randn(M, cfg["hid"]).half().pin_memory()
+        yh = torch.empty(M, packed[-1].N, dtype=torch.float16).pin_memory()
+        xd = torch.empty(M, cfg["hid"], device=dev, dtype=torch.float16)
 
         def step_e2e():
             xd.copy_(xh, non_blocking=True)
@@ -363,111 +488,99 @@ def main():
             torch.cuda.current_stream().synchronize()
 
         ms_e2e, _ = timed(step_e2e, max(2, args.steps // 2), 1)
-        e2e = {"value": tokens_per_step / (ms_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": xh.numel() * 2,
+        e2e = {"value": M * world / (ms_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": xh.numel() * 2,
                "d2h_bytes_per_step": yh.numel() * 2, "ms_per_step": ms_e2e,
-               "api": "PackedLinear.forward (pbl_linear_forward) per linear; inputs from pinned host memory each step"}
+               "api": f"{type(mods[0]).__name__}.__call__ (modules installed by "
+                      f"{'replace_from_fakequant' if cfg['method'] == 'gptq_pb' else 'replace_with_qlinear'} + pack_model) per linear; "
+                      "inputs from pinned host memory each step"}
 
     # -- decode regime (batch x 1 token): the HBM-bound bit-plane kernel ------------------------------------------------
     decode = None
     if not args.no_decode:
         Md = args.batch
         xd_in = {k: v[:Md].contiguous() for k, v in xin.items()}
-        douts = [torch.empty(Md, p.N, device=dev, dtype=torch.float16) for p in layers[0]]
 
+        @torch.no_grad()
         def dstep():
-            for row in layers:
-                for i, p in enumerate(row):
-                    p.forward(xd_in[SHAPES[i][3]], out=douts[i])
+            for blk in blocks:
+                for m, src in blk:
+                    m(xd_in[src])
+
+        def graphed(fn):
+            graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            with torch.cuda.stream(side):
+                fn()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(graph, stream=side):
+                    fn()
+            return graph
 
         ms_d_eager, _ = timed(dstep, 20, 3)
-        # the decode step is launch-bound from Python (224 kernels of a few microseconds): replay it as a CUDA graph
-        graph = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream()
-        with torch.cuda.stream(side):
-            dstep()
-            torch.cuda.synchronize()
-            with torch.cuda.graph(graph, stream=side):
-                dstep()
-        ms_d, _ = timed(graph.replay, 50, 5)
-        # batch-1 decode (the classic GEMV regime) for reference
+        # the decode step is launch-bound from Python (hundreds of kernels of a few microseconds): replay it as a CUDA graph
+        ms_d, _ = timed(graphed(dstep).replay, 50, 5)
         x1_in = {k: v[:1].contiguous() for k, v in xin.items()}
-        d1outs = [torch.empty(1, p.N, device=dev, dtype=torch.float16) for p in layers[0]]
 
+        @torch.no_grad()
         def d1step():
-            for row in layers:
-                for i, p in enumerate(row):
-                    p.forward(x1_in[SHAPES[i][3]], out=d1outs[i])
+            for blk in blocks:
+                for m, src in blk:
+                    m(x1_in[src])
 
-        graph1 = torch.cuda.CUDAGraph()
-        with torch.cuda.stream(side):
-            d1step()
-            torch.cuda.synchronize()
-            with torch.cuda.graph(graph1, stream=side):
-                d1step()
-        ms_d1, _ = timed(graph1.replay, 50, 5)
-        # sibling fusion (what a model-level integration can do on top of the drop-in modules): q/k/v and gate/up
-        # share their input, so their weights can be packed as ONE layer each (rows concatenated before packing):
-        # 4 launches per decoder layer instead of 7.
-        ms_d_fused = None
-        if not rowshard and args.layers <= NLAYERS:
-            flayers = []
-            for li in range(args.layers):
-                ws_, ms_ = [], []
-                for si, (name, N, K, src) in enumerate(SHAPES):
-                    w, low = synth_layer_gpu(N, K, args.low_frac, 1000 * li + si, dev)
-                    ws_.append(w)
-                    ms_.append(low)
-                grp = [(0, 1, 2), (3,), (4, 5), (6,)]
-                flayers.append([(pb.PackedLinear.from_dense(torch.cat([ws_[i] for i in gidx]), None, torch.cat([ms_[i] for i in gidx])),
-                                 SHAPES[gidx[0]][3]) for gidx in grp])
-                del ws_, ms_
-            fouts = [torch.empty(Md, p.N, device=dev, dtype=torch.float16) for p, _ in flayers[0]]
-
-            def fstep():
-                for row in flayers:
-                    for i, (p, src) in enumerate(row):
-                        p.forward(xd_in[src], out=fouts[i])
-
-            fgraph = torch.cuda.CUDAGraph()
-            with torch.cuda.stream(side):
-                fstep()
-                torch.cuda.synchronize()
-                with torch.cuda.graph(fgraph, stream=side):
-                    fstep()
-            ms_d_fused, _ = timed(fgraph.replay, 50, 5)
-            del flayers
+        ms_d1, _ = timed(graphed(d1step).replay, 50, 5)
         G = 1
-        b_bin = nk / 8 + 4 * sum(p.N for row in layers for p in row) * G + 2 * Md * sum(p.K + p.N for row in layers for p in row)
-        b_sal = 2 * nnz + sum(p.N + 1 for row in layers for p in row)
+        b_bin = nk / 8 + 4 * sum(p.N for p in packed) * G + 2 * Md * sum(p.K + p.N for p in packed)
+        b_sal = 2 * nnz + sum(p.N + 1 for p in packed)
         ach = (b_bin + b_sal) / (ms_d * 1e-3) / 1e9
-        decode = {"tokens_per_s": Md * (1 if rowshard else world) / (ms_d * 1e-3), "ms_per_step": ms_d,
+        tr = ncu_traffic("decode") if (args.config == "llama7b" and Md == 8 and args.low_frac == 0.9) else None
+        # sibling fusion through the module API (pb.fuse_siblings): q/k/v and gate/up packed as ONE layer each
+        ms_d_fused = None
+        if cfg["family"] == "llama":
+            import torch.nn as nn
+            holders = []
+            for blk in blocks:
+                h = nn.Module()
+                for (m, _src), (name, *_r) in zip(blk, shapes):
+                    setattr(h, name, m)
+                holders.append(h)
+            with torch.no_grad():
+                nf = sum(pb.fuse_siblings(h) for h in holders)
+            fblocks = [[(getattr(h, name), src) for name, _, _, src in shapes] for h in holders]
+
+            @torch.no_grad()
+            def fstep():
+                for blk in fblocks:
+                    for m, src in blk:
+                        m(xd_in[src])
+
+            ms_d_fused, _ = timed(graphed(fstep).replay, 50, 5)
+            del fblocks, holders
+        decode = {"tokens_per_s": Md * world / (ms_d * 1e-3), "ms_per_step": ms_d,
                   "ms_per_step_eager_python_launch": ms_d_eager, "batch": Md, "ms_per_step_batch1": ms_d1,
-                  "batch1_actual_bytes_gbs": packed_bytes / (ms_d1 * 1e-3) / 1e9,
-                  "ms_per_step_fused_siblings": ms_d_fused, "launch": "CUDA graph replay of the 224 launches",
-                  "kernel": {4: "pbl decode kernel (positioned salient entries, warp-granular stream-K, mma.sync)",
-                             2: "pbl mma.sync bit-plane skinny kernel"}.get(layers[0][0].select_kernel(Md), "pbl CUDA-core bit-plane kernel"),
+                  "ms_per_step_fused_siblings": ms_d_fused,
+                  "fused_siblings_note": "pb.fuse_siblings(model): q/k/v and gate/up as one packed layer each (4 launches per decoder layer)",
+                  "launch": f"CUDA graph replay of the {len(mods)} module calls",
+                  "kernel": "pbl decode kernel (sign-bit XOR +1.0 tile fragments, positioned salient entries, warp-granular stream-K, mma.sync)",
                   "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                               # dram__bytes_read+write per launch from the committed ncu --set full capture of the same
-                               # launches (profiles/r01_decode_kernel_M8_llama7b_shapes.md): 9.24 MB (4096x4096), 24.53 MB
-                               # (11008x4096), 24.35 MB (4096x11008) -> average over the 7 linears of a decoder layer
-                               "traffic": ((4 * 9.2352e6 + 2 * 24.526848e6 + 24.348672e6) / 7.0) if (layers[0][0].select_kernel(Md) == 4 and Md == 8 and args.low_frac == 0.9) else None,
-                               "algorithmic_bytes_per_launch": (b_bin + b_sal) / max(1, sum(len(r) for r in layers)),
+                               "traffic": None if tr is None else tr["bytes_per_launch"], "traffic_note": tr,
+                               "algorithmic_bytes_per_launch": (b_bin + b_sal) / len(mods),
                                "algorithmic_bytes_per_step": b_bin + b_sal,
-                               "actual_packed_bytes": packed_bytes, "decode_index_bytes": dindex_bytes,
+                               "actual_packed_bytes": packed_bytes,
                                "actual_bytes_gbs": packed_bytes / (ms_d * 1e-3) / 1e9,
+                               "frac_fused_siblings": None if ms_d_fused is None else (b_bin + b_sal) / (ms_d_fused * 1e-3) / 1e9 / pk["hbm"],
                                "peak_source": pk["src"]}}
 
     # -- the literal XNOR-popcount kernel (BiRealLinear format: alpha*sign(W), binarized activations) ---------------
     xnor = None
-    if not args.no_decode and not rowshard:
+    if not args.no_decode and cfg["family"] == "llama" and args.config == "llama7b":
         Md = args.batch
         blayers = []
         for li in range(args.layers):
             row = []
-            for si, (name, N, K, src) in enumerate(SHAPES):
+            for si, (name, N, K, src) in enumerate(shapes):
                 gq = torch.Generator(device=dev).manual_seed(7000 * li + si)
                 w = torch.randn(N, K, device=dev, generator=gq)
-                row.append(pb.PackedLinear.from_dense((w.abs().mean(1, keepdim=True) * torch.sign(w)).half()))
+                row.append(pb.PackedLinear.from_dense(w.abs().mean(1, keepdim=True) * torch.sign(w)))     # fp32: planes layout
                 del w
             blayers.append(row)
         xb_in = {k: v[:Md].contiguous() for k, v in xin.items()}
@@ -477,7 +590,7 @@ def main():
         def bstep():
             for row in blayers:
                 for i, p in enumerate(row):
-                    p.bireal_forward(xb_in[SHAPES[i][3]], out=bouts[i], workspace=bws)
+                    p.bireal_forward(xb_in[shapes[i][3]], out=bouts[i], workspace=bws)
 
         bgraph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
@@ -489,7 +602,8 @@ def main():
         ms_b, _ = timed(bgraph.replay, 50, 5)
         nb = sum(p.N for row in blayers for p in row)
         kb_ = sum(p.K for row in blayers for p in row)
-        b_alg = nk / 8 + 8 * nb + Md * (2 * kb_ + 4 * nb)       # sign plane + {lo,hi} + fp16 x in + fp32 y out
+        nkb = sum(p.N * p.K for row in blayers for p in row)
+        b_alg = nkb / 8 + 8 * nb + Md * (2 * kb_ + 4 * nb)       # sign plane + {lo,hi} + fp16 x in + fp32 y out
         ach = b_alg / (ms_b * 1e-3) / 1e9
         xnor = {"what": "BiRealLinear forward (quant/quantizer.py:151-169) as XNOR-popcount over the packed sign plane, "
                         "Llama-7B shapes, 224 launches + 224 activation-binarize launches per step, CUDA graph replay",
@@ -498,26 +612,123 @@ def main():
                              "traffic": None, "algorithmic_bytes_per_step": b_alg, "peak_source": pk["src"]}}
         del blayers
 
+    # -- N > 1: the north star's row-sharded linears, measured beside the replicas ------------------------------------
+    rowshard = None
+    if world > 1 and not args.no_rowshard and cfg["method"] == "gptq_pb":
+        del blocks, mods, packed
+        torch.cuda.empty_cache()
+        rowshard = run_rowshard(pb, cfg, args, dev, rank, world, timed, M)
+
     stop.set()
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb = cpu_baseline()
+        cb = cpu_baseline(cfg, args)
         cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if rowshard else "weak",
+        line = {"metric": metric_name(cfg, args), "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-                "config": {"workload": workload_name(args), "tokens_per_step_per_gpu": M,
-                           "parallelism": (f"rowshard{world}+allgather" if rowshard else f"dp{world} (replicas, no collective)"),
-                           "l2": "per-step working set (2.3 GB packed weights + activations) >> 126 MB L2; no flush needed",
-                           "packed_bytes": packed_bytes, "decode_index_bytes": dindex_bytes, "bits_per_weight": 8.0 * packed_bytes / nk * (world if rowshard else 1),
-                           "salient_fraction": nnz / nk * (world if rowshard else 1), "model_build_s": build_s},
+                "config": {"workload": workload_name(cfg, args), "tokens_per_step_per_gpu": M,
+                           "parallelism": f"dp{world} (token-sharded replicas, no data-path collective)" + ("; `rowshard` = the row-sharded split" if rowshard else ""),
+                           "l2": f"per-step working set ({packed_bytes / 1e9:.2f} GB packed weights + activations) >> 126 MB L2; no flush needed",
+                           "packed_bytes": packed_bytes, "bits_per_weight": 8.0 * packed_bytes / nk,
+                           "bits_per_weight_note": "every resident device buffer of every layer (sign words, entries, offsets, level tables, exceptions); there is one copy",
+                           "salient_fraction": nnz / nk, "model_build_s": build_s,
+                           "api": "drop-in nn.Modules installed by the surgery functions, called as module(x)"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks_summary(samples), "roofline": roofline,
-                "cpu_baseline": cb, "decode": decode, "xnor_popcount": xnor, "parity": parity}
+                "cpu_baseline": cb, "decode": decode, "xnor_popcount": xnor, "rowshard": rowshard, "parity": parity}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_rowshard(pb, cfg, args, dev, rank, world, timed, M):
+    """BASELINE configs[3]: the same model with every linear's output rows split across the ranks (low_frac 0.95),
+    x replicated. Prefill: rank-local GEMM + NCCL all-gather per linear (bandwidth-bound on NVLink: SURVEY 8e).
+    Per-token regime: pbl_linear_forward_push -- the decode kernel stores its slice into every rank's output buffer and
+    completes with in-kernel flags; no collective call."""
+    import torch.distributed as dist
+    from pbllm_b200.sharding import PeerContext, PushLinear, RowShardedLinear, shard_rows
+    shapes = layer_shapes(cfg)
+    lf = args.rowshard_low_frac
+    Md = args.batch
+    ctx = PeerContext(dev, arena_bytes=max(64 << 20, 2 * 16 * sum(N for _, N, _, _ in shapes) * 2))
+    push_layers, ag_layers = [], []
+    outs_off = {}
+    for li in range(args.layers):
+        prow, arow = [], []
+        for si, (name, N, K, src) in enumerate(shapes):
+            w, low = synth_layer_gpu(N, K, lf, 1000 * li + si, dev)
+            pl = PushLinear.__new__(PushLinear)
+            # one output region per linear NAME, reused by every decoder layer (a rank is never more than one linear ahead)
+            r0, r1, n_loc = shard_rows(N, world, rank)
+            p = pb.PackedLinear.from_dense(w[r0:r1], None, low[r0:r1])
+            if name not in outs_off:
+                outs_off[name] = ctx.alloc(16 * N * 2)
+            pl.ctx, pl.N, pl.K, pl.r0, pl.r1, pl.n_loc, pl.p, pl.max_tokens, pl.es = ctx, N, K, r0, r1, n_loc, p, 16, 2
+            pl.out_off = outs_off[name]
+            pl.out = ctx.arena[pl.out_off:pl.out_off + 16 * N * 2].view(torch.float16).view(16, N)
+            pl._desc = {True: ctx.push_desc(pl.out_off, r0 * 2, True), False: ctx.push_desc(pl.out_off, r0 * 2, False)}
+            prow.append((pl, src))
+            arow.append((RowShardedLinear(p.forward, N, K, rank, world), src))
+            del w, low
+        push_layers.append(prow)
+        ag_layers.append(arow)
+    torch.cuda.synchronize()
+    dist.barrier()
+    g = torch.Generator(device=dev).manual_seed(99)             # replicated activations: the same on every rank
+    xin = {"h": torch.randn(M, cfg["hid"], device=dev, generator=g).half(), "a": torch.randn(M, cfg["hid"], device=dev, generator=g).half(),
+           "f": torch.randn(M, cfg["ffn"], device=dev, generator=g).half()}
+    xd = {k: v[:Md].contiguous() for k, v in xin.items()}
+
+    # parity of the gathered outputs against fp64 dense math over the full (unsharded) weight, first decoder layer
+    err = 0.0
+    for si, (name, N, K, src) in enumerate(shapes):
+        w, _low = synth_layer_gpu(N, K, lf, si, dev)
+        y = push_layers[0][si][0].forward(xd[src])
+        ctx.wait()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ref = xd[src].double() @ w.double().t()
+        err = max(err, float((y.double() - ref).abs().max() / ref.abs().max()))
+        dist.barrier()
+        del w
+
+    def dstep():
+        for row in push_layers:
+            for pl, src in row:
+                pl.forward(xd[src])
+        ctx.wait()
+
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        dstep()
+        torch.cuda.synchronize()
+        dist.barrier()
+        with torch.cuda.graph(graph, stream=side):
+            dstep()
+    ms_d, _ = timed(graph.replay, 50, 5)
+
+    @torch.no_grad()
+    def pstep():
+        for row in ag_layers:
+            for m, src in row:
+                m(xin[src])
+
+    ms_p, _ = timed(pstep, 2, 1)
+    gathered = 2 * M * sum(N for _, N, _, _ in shapes) * args.layers * (world - 1) / world
+    return {"what": f"row-sharded linears across {world} GPUs, low_frac={lf} (BASELINE configs[3]); x replicated, one gather per linear",
+            "parallelism": f"rowshard{world}", "scaling": "strong",
+            "decode": {"ms_per_step": ms_d, "tokens_per_s": Md / (ms_d * 1e-3), "batch": Md,
+                       "gather": "fused: decode-kernel epilogue stores into every rank's buffer over NVLink (peer-mapped symmetric memory) "
+                                 "+ in-kernel epoch flags; no NCCL call", "launch": "CUDA graph replay",
+                       "parity_max_rel_err_vs_fp64_dense": err},
+            "prefill": {"ms_per_step": ms_p, "tokens_per_s": M / (ms_p * 1e-3), "tokens_per_step": M,
+                        "gather": "ncclAllGather (torch.distributed.all_gather_into_tensor) + layout copy per linear",
+                        "gathered_bytes_per_rank_per_step": gathered,
+                        "nvlink_gbs": gathered / (ms_p * 1e-3) / 1e9}}
 
 
 if __name__ == "__main__":

@@ -10,9 +10,9 @@ from .quant import (BinaryInterface, BinaryLinear, BiRealLinear, FdaBinaryLinear
                     BinaryXnorExceptOutliersLinear, BinaryXnorExceptOutliersLinearHessian, PackedFakeQuantLinear,
                     weight_quant_8bit)
 from .surgery import (replace_with_qlinear, to_regular_linear, save_bnn, load_bnn, replace_from_fakequant,  # noqa: F401
-                      pack_model, save_packed, load_packed, from_reference)
+                      pack_model, save_packed, load_packed, from_reference, fuse_siblings)
 
 __all__ = ["PackedLinear", "pack_sizes", "BinaryInterface", "BinaryLinear", "BiRealLinear", "FdaBinaryLinear", "IrBinaryLinear",
            "XnorBinaryLinear", "BinaryXnorExceptOutliersLinear", "BinaryXnorExceptOutliersLinearHessian",
            "PackedFakeQuantLinear", "weight_quant_8bit", "replace_with_qlinear", "to_regular_linear", "save_bnn",
-           "load_bnn", "replace_from_fakequant", "pack_model", "save_packed", "load_packed", "from_reference"]
+           "load_bnn", "replace_from_fakequant", "pack_model", "save_packed", "load_packed", "from_reference", "fuse_siblings"]

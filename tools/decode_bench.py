@@ -1,8 +1,8 @@
 """Decode-regime micro-benchmark: a few decoder layers' worth of Llama-7B-shaped PB linears (distinct weights per
 layer, working set > L2), batch M tokens, replayed as one CUDA graph.  Run once per variant; the variant knobs are
 environment variables read by libpbllm.so at first use:
-    PBL_FORCE_KERNEL=2|4   old skinny kernel / decode kernel        PBL_DK_CTAS=1..4   decode grid = SMs x this
-    PBL_DK_OCC=3|4         register budget (85 / 64 regs)           PBL_PDL=0|1        programmatic dependent launch
+    PBL_DK_CTAS=1..4   decode grid = SMs x this        PBL_DK_OCC=2|3   register budget (128 / 80 regs)
+    PBL_PDL=0|1        programmatic dependent launch
 Prints one JSON line."""
 import argparse
 import json
@@ -14,7 +14,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import pbllm_b200 as pb  # noqa: E402
-from bench import SHAPES, synth_layer_gpu  # noqa: E402
+from bench import CONFIGS, layer_shapes, synth_layer_gpu  # noqa: E402
+
+SHAPES = layer_shapes(CONFIGS["llama7b"])
 
 
 def main():

@@ -10,7 +10,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import pbllm_b200 as pb  # noqa: E402
-from bench import SHAPES, synth_layer_gpu  # noqa: E402
+from bench import CONFIGS, layer_shapes, synth_layer_gpu  # noqa: E402
+
+SHAPES = layer_shapes(CONFIGS["llama7b"])
 
 STRIDE = 16 * 148 * 8 * 8
 
