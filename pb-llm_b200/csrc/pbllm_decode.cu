@@ -21,8 +21,10 @@
 //  * warp-granular stream-K (unchanged): the blocks of the layer are dealt out in contiguous, equal (+-1) runs to the warps
 //    of a fixed grid, partial row groups are reduced across the CTA's warps in shared memory and across CTAs through a
 //    small zeroed workspace with tagged 64-bit slots, summed in CTA order (deterministic).
-//  * every weight-side load of a warp's first blocks is issued before griddepcontrol.wait: under programmatic dependent
-//    launch the packed stream of layer i+1 is in flight while layer i still computes.
+//  * the packed stream (sign words + entries of a warp's next blocks) is moved by the bulk-copy engine (cp.async.bulk ->
+//    UBLKCP) into a per-warp shared-memory ring, three blocks deep, completed on mbarriers: no registers are spent on
+//    prefetch, so 24 warps per SM fit.  The first copies are issued before griddepcontrol.wait: under programmatic
+//    dependent launch the packed stream of layer i+1 is in flight while layer i still computes.
 #include <cstdlib>
 #include <type_traits>
 
@@ -37,7 +39,15 @@ constexpr int kThreads = kWarps * 32;
 constexpr int kTok = 8;                       // tokens per group (mma N)
 constexpr int kTileBytes = kRgRows * kTileCols * 2;   // 4096: the warp's 32x64 16-bit tile (128B rows, swizzled)
 constexpr int kHeadBytes = kRgRows * kTok * 4;        // 1024 per token group: the warp's head-segment partial (fp32 [tokens][32 rows])
-constexpr int kWarpBytes = kTileBytes + kHeadBytes;   // 5120 (one token group per pass); two groups: + kHeadBytes
+// per-warp ring of the packed stream: kStages blocks in flight, each = 256 B of sign words + up to kEntCap 16-byte entry units
+// (blocks with more entries read the rest straight from global memory), filled by cp.async.bulk, completed on mbarriers
+constexpr int kStages = 3;
+constexpr int kEntCap = 64;
+constexpr int kStageBytes = 256 + kEntCap * 16;       // 1280
+constexpr int kRingBytes = kStages * kStageBytes + 128;  // + the stages' mbarriers, padded: the tile's XOR-swizzled addressing
+                                                         // needs every warp's region to start 128-byte aligned
+constexpr int kWarpBytes = kTileBytes + kHeadBytes + kRingBytes;   // 9088 (one token group per pass); two groups: + kHeadBytes
+static_assert(kWarpBytes % 128 == 0 && kHeadBytes % 128 == 0, "per-warp regions must keep the tile 128-byte aligned");
 constexpr int kOut = kRgRows * kTok;          // 256 outputs per (row group, token group) == kThreads
 static_assert(kOut == kThreads, "one thread per output in the cross-warp reduction");
 
@@ -117,6 +127,22 @@ __device__ __forceinline__ void dk_unpatch4(const uint32_t tile_s, const uint4 e
     sts_u16(tile_s + (e.w >> 20), one);
 }
 
+__device__ __forceinline__ void dk_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint2 dk_lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 dk_lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ unsigned long long dk_now() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -169,13 +195,28 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     // below up to griddepcontrol.wait touches only immutable packed weights.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    // first loads of this warp's stream: sign words and entry offsets of its run (eptr lives in registers, one per lane)
-    const uint2* sgp = p.fsign + (size_t)w_lo * kRgRows + lane;
-    uint2 sg = make_uint2(0, 0);
+    // this warp's ring and its mbarriers
+    const uint32_t ring_s = tile_s + kTileBytes + kNT * kHeadBytes, bar_s = ring_s + kStages * kStageBytes;
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < kStages; ++st) mbar_init(bar_s + 8u * st, 1);
+        fence_barrier_init();
+    }
+    // entry offsets of the run: eptr lives in registers, one per lane (refilled every 28 blocks)
     uint32_t epr = 0;
-    if (w_lo < w_hi) {
-        sg = __ldg(sgp);
-        if (w_lo + lane <= w_hi) epr = __ldg(p.eptr + w_lo + lane);
+    if (w_lo < w_hi && w_lo + lane <= w_hi) epr = __ldg(p.eptr + w_lo + lane);
+    __syncwarp();
+    // producer side (lane 0): one block = its 256 B of sign words + its first min(n4, kEntCap) entry units
+    auto issue = [&](uint32_t blk, uint32_t st, uint32_t eb, uint32_t n4) {
+        const uint32_t n = min(n4, (uint32_t)kEntCap), dst = ring_s + st * kStageBytes, bar = bar_s + 8u * st;
+        mbar_arrive_expect_tx(bar, 256u + n * 16u);
+        dk_bulk_g2s(dst, p.fsign + (size_t)blk * kRgRows, 256u, bar);
+        if (n) dk_bulk_g2s(dst + 256u, p.ent + eb, n * 16u, bar);
+    };
+#pragma unroll
+    for (int st = 0; st < kStages; ++st) {              // fill the ring: kStages blocks of DRAM latency in flight at once
+        const uint32_t eb = __shfl_sync(0xffffffffu, epr, st), n4 = __shfl_sync(0xffffffffu, epr, st + 1) - eb;
+        if (lane == 0 && w_lo + st < w_hi) issue(w_lo + st, st, eb, n4);
     }
     uint32_t rg = 0, kb = 0;
     if (w_lo < w_hi) { rg = w_lo / TC; kb = w_lo - rg * TC; }
@@ -212,23 +253,7 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     }
 
     uint32_t ci = 0;                               // index of the current block in the eptr register chunk
-    // the first min(n4, 64) units of a block sit in two register sets of h1 = ceil/2 and the rest: unit `lane` and unit
-    // `h1 + lane` (the packer deals entries to units so that each of the 8 patch stores is bank-conflict free)
-    struct Ent { uint4 a, c; uint32_t eb, n4; };        // one block's entries: units `lane` and `h1 + lane`, offset, unit count
-    auto ent_load = [&](Ent& E, uint32_t i) {           // i = index of the block in this warp's eptr register chunk
-        E.eb = __shfl_sync(0xffffffffu, epr, i);
-        E.n4 = __shfl_sync(0xffffffffu, epr, i + 1u) - E.eb;
-        const uint32_t n1 = min(E.n4, 64u), h1 = (n1 + 1u) >> 1;
-        const uint4* e = p.ent + (E.eb + lane);
-        asm volatile("" : "+l"(e));                     // one address computation for both predicated loads
-        if (lane < h1) E.a = __ldg(e);
-        if (lane + h1 < n1) E.c = __ldg(e + h1);
-    };
-    Ent E0, E1;                                         // two blocks of entries in flight: each set is reloaded for the block
-    E0.a = E0.c = E1.a = E1.c = make_uint4(0, 0, 0, 0); // after next right after its un-patch -- two blocks of cover
-    E0.eb = E0.n4 = E1.eb = E1.n4 = 0;
-    if (w_lo < w_hi) ent_load(E0, 0);
-    if (w_lo + 1u < w_hi) ent_load(E1, 1);
+    uint32_t cs = 0, cph = 0;                      // ring stage of the current block and the parity its mbarrier completes with
 
     // ---- activation loads: lane -> (token = lane>>2, 16-column segment = lane&3) of the 8 x 64 block ----------
     const uint32_t xtok = lane >> 2, xseg = lane & 3u;
@@ -364,11 +389,10 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     if (w_lo < w_hi) load_x_next(X0);
     __syncwarp();                                       // the initialised tile is visible to the whole warp
 
-    // Every stream is prefetched into registers: sign words one block ahead (reloaded in place), activations one block
-    // ahead (two register sets), salient entries -- the stream that comes from DRAM with a dependent address -- two blocks
-    // ahead (two sets; each is reloaded right after its un-patch).
+    // The packed stream arrives through the ring (three blocks ahead, no registers); the activations are loaded one block
+    // ahead into a second register set.
     const uint16_t one16 = (uint16_t)kOne2;
-    auto do_block = [&](const uint32_t blk, Ent& E, const XF& X, XF& Xn) {
+    auto do_block = [&](const uint32_t blk, const XF& X, XF& Xn) {
         const bool more = blk + 1 < w_hi;
         if (grouped) {
             const uint32_t g = kb / p.tiles_per_group;
@@ -379,13 +403,27 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
             }
         }
         if (more) load_x_next(Xn);                      // the next block's activations: a whole block of cover
+        if (ci + (uint32_t)kStages + 1u > 31u) {        // rare: refill the eptr registers (runs longer than 28 blocks)
+            if (blk + lane <= w_hi) epr = __ldg(p.eptr + blk + lane);
+            ci = 0;
+        }
+        const uint32_t eb = __shfl_sync(0xffffffffu, epr, ci), n4 = __shfl_sync(0xffffffffu, epr, ci + 1u) - eb;
+        const uint32_t n1 = min(n4, (uint32_t)kEntCap), h1 = (n1 + 1u) >> 1;
+        const uint32_t stage = ring_s + cs * kStageBytes;
 
-        // salient entries into the tile
-        const uint32_t n1 = min(E.n4, 64u), h1 = (n1 + 1u) >> 1;
-        if (lane < h1) dk_patch4(tile_s, E.a);
-        if (lane + h1 < n1) dk_patch4(tile_s, E.c);
-        for (uint32_t i = 64u + lane; i < E.n4; i += 32u) dk_patch4(tile_s, __ldg(p.ent + (E.eb + i)));   // rare: > 256 salient in a block
-        __syncwarp();                                   // the patched tile is complete and visible to the whole warp
+        // this block's record has landed: sign words and salient entries out of the ring, entries into the tile
+        mbar_wait(bar_s + 8u * cs, cph);
+        const uint2 sg = dk_lds64(stage + lane * 8u);
+        uint4 ea = make_uint4(0, 0, 0, 0), ec = make_uint4(0, 0, 0, 0);
+        if (lane < h1) { ea = dk_lds128(stage + 256u + lane * 16u); dk_patch4(tile_s, ea); }
+        if (lane + h1 < n1) { ec = dk_lds128(stage + 256u + (lane + h1) * 16u); dk_patch4(tile_s, ec); }
+        for (uint32_t i = (uint32_t)kEntCap + lane; i < n4; i += 32u) dk_patch4(tile_s, __ldg(p.ent + (eb + i)));   // rare: > 256 salient in a block
+        __syncwarp();                                   // the patched tile is complete; every lane is done reading the stage
+        {                                               // refill the stage with the block kStages ahead
+            const uint32_t eb2 = __shfl_sync(0xffffffffu, epr, ci + (uint32_t)kStages);
+            const uint32_t n42 = __shfl_sync(0xffffffffu, epr, ci + (uint32_t)kStages + 1u) - eb2;
+            if (lane == 0 && blk + (uint32_t)kStages < w_hi) issue(blk + (uint32_t)kStages, cs, eb2, n42);
+        }
 
         // the block on the tensor cores: A fragments = tile words with the sign bits XORed in, B fragments = the activation registers
         const uint32_t xw[8] = {X.a.x, X.a.y, X.a.z, X.a.w, X.b.x, X.b.y, X.b.z, X.b.w};
@@ -409,21 +447,14 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
                 if constexpr (kNT == 2) dk_mma<T>(acc_x2, kOne2, kOne2, kOne2, kOne2, xw2[2 * qi], xw2[2 * qi + 1]);
             }
         }
-        sgp += more ? kRgRows : 0;                      // unconditional reload (the last block re-reads itself): the load
-        sg = __ldg(sgp);                                // must land in `sg` directly, not in a temporary that is moved at once
 
         __syncwarp();                                   // every lane's ldmatrix reads are done: reset the entries to +1.0
-        if (lane < h1) dk_unpatch4(tile_s, E.a, one16);
-        if (lane + h1 < n1) dk_unpatch4(tile_s, E.c, one16);
-        for (uint32_t i = 64u + lane; i < E.n4; i += 32u) dk_unpatch4(tile_s, __ldg(p.ent + (E.eb + i)), one16);
+        if (lane < h1) dk_unpatch4(tile_s, ea, one16);
+        if (lane + h1 < n1) dk_unpatch4(tile_s, ec, one16);
+        for (uint32_t i = (uint32_t)kEntCap + lane; i < n4; i += 32u) dk_unpatch4(tile_s, __ldg(p.ent + (eb + i)), one16);
         ++ci;
-        if (blk + 2u < w_hi) {                          // this set's next block is the one after next
-            if (ci + 2u > 31u) {                        // rare: refill the eptr registers (runs longer than 30 blocks)
-                if (blk + 1u + lane <= w_hi) epr = __ldg(p.eptr + blk + 1u + lane);
-                ci = 0;
-            }
-            ent_load(E, ci + 1u);
-        }
+        ++cs;
+        if (cs == (uint32_t)kStages) { cs = 0; cph ^= 1u; }
         __syncwarp();                                   // the resets land before the next block's patch stores (other lanes, same slots)
 
         ++kb;
@@ -475,9 +506,9 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
             }
         }
     };
-    for (uint32_t blk = w_lo; blk < w_hi; blk += 2u) {   // unrolled by two: the register sets alternate without moves
-        do_block(blk, E0, X0, X1);
-        if (blk + 1u < w_hi) do_block(blk + 1u, E1, X1, X0);
+    for (uint32_t blk = w_lo; blk < w_hi; blk += 2u) {   // unrolled by two: the activation register sets alternate without moves
+        do_block(blk, X0, X1);
+        if (blk + 1u < w_hi) do_block(blk + 1u, X1, X0);
     }
 
     // ---- cross-warp reduction in shared memory; row groups shared with other CTAs go through the workspace ----------
@@ -624,7 +655,7 @@ static int dk_occupancy() {      // which register budget / launch-bounds varian
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("PBL_DK_OCC");
-        v = (e && *e) ? atoi(e) : 2;                  // 2 -> up to 128 registers (no spills), 3 -> 80 registers
+        v = (e && *e) ? atoi(e) : 2;                  // 2 -> up to 128 registers, 16 warps per SM (measured best); 3 -> 80 registers, 24 warps
         if (v != 3) v = 2;
     }
     return v;
