@@ -232,6 +232,18 @@ PBL_API size_t pbl_bireal_fixup_workspace(const pbl_layer* layer, int64_t M);
 PBL_API int pbl_bireal_forward_ws(const pbl_layer* layer, const void* x, int64_t ldx, int x_dtype, float* y, int64_t ldy,
                                   int64_t M, void* workspace, void* fixup_workspace, size_t fixup_workspace_bytes, void* stream);
 
+/* ---- GPTQ-PB calibration: the column loop of LowHighGPT.fasterquant (gptq_pb/gptq.py:116-168) for ONE block
+ *      of nc <= 128 columns, all rows, as one kernel.  W1 [N][ldw] fp32 holds the block's current weights and receives the
+ *      quantised values Q1 (gptq.py:166); err_out [N][lde] receives Err1 (gptq.py:163) for the caller's cross-block update
+ *      W[:, col_ed:] -= Err1 @ Hinv[col_st:col_ed, col_ed:] (gptq.py:168); hinv_block = Hinv[col_st:col_ed, col_st:col_ed]
+ *      (upper Cholesky factor of the inverse Hessian, row stride ldh); mask1 [N][ldm] nonzero = low (binarized) position
+ *      (gptq.py:92,99); per-row parameters: the xnor low quantizer's mean / scale of the block's group (low_quant.py:25-32) and
+ *      the 8-bit high quantizer's scale / zero (high_quant.py:29-67); losses [N] (optional) accumulates gptq.py:167. ---- */
+PBL_API int pbl_gptq_block(float* W1, int64_t ldw, float* err_out, int64_t lde, const float* hinv_block, int64_t ldh,
+                           const uint8_t* mask1, int64_t ldm, const float* low_mean, const float* low_scale,
+                           const float* high_scale, const float* high_zero, float maxq, int64_t N, int nc, float* losses,
+                           void* stream);
+
 /* Which kernel pbl_linear_forward would launch for this (layer, M): 0 = CUDA-core bit-plane kernel (fp32 layers),
  * 1 = two-phase prefill (expansion + tcgen05 GEMM; fp16 / bf16 layers, M above PBL_DECODE_MAX_M, default 64),
  * 4 = decode kernel.  PBL_FORCE_KERNEL=0|1|4 overrides (tests). */

@@ -274,6 +274,21 @@ int pbl_peer_wait(const pbl_peer_push* push, void* stream) {
     return launch_peer_wait(*push, (cudaStream_t)stream);
 }
 
+int pbl_gptq_block(float* W1, int64_t ldw, float* err_out, int64_t lde, const float* hinv_block, int64_t ldh, const uint8_t* mask1,
+                   int64_t ldm, const float* low_mean, const float* low_scale, const float* high_scale, const float* high_zero,
+                   float maxq, int64_t N, int nc, float* losses, void* stream) {
+    if (!W1 || !err_out || !hinv_block || !mask1 || !low_mean || !low_scale || !high_scale || !high_zero) {
+        set_error("pbl_gptq_block: null pointer"); return PBL_ERR_NULL;
+    }
+    if (N <= 0 || nc <= 0 || nc > 128 || ldw < nc || lde < nc || ldh < nc || ldm < nc) {
+        set_error("pbl_gptq_block: bad shape (N=%lld, nc=%d must be 1..128, leading dimensions >= nc)", (long long)N, nc); return PBL_ERR_SHAPE;
+    }
+    int rc = device_check_impl();
+    if (rc) return rc;
+    return launch_gptq_block(W1, ldw, err_out, lde, hinv_block, ldh, mask1, ldm, low_mean, low_scale, high_scale, high_zero, maxq, N, nc,
+                             losses, (cudaStream_t)stream);
+}
+
 int pbl_stream_layout(int64_t N, int64_t K, int64_t groupsize, int dtype, pbl_stream_sizes* out) {
     if (!out) { set_error("pbl_stream_layout: out is NULL"); return PBL_ERR_NULL; }
     if (dtype != PBL_F16 && dtype != PBL_BF16) { set_error("the block-stream layout holds fp16 / bf16 layers"); return PBL_ERR_DTYPE; }

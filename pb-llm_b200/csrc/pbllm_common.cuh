@@ -85,6 +85,9 @@ void decode_plan(int64_t N, int64_t K, int64_t M, int sms, int ctas_per_sm, uint
 int launch_decode(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws, size_t ws_bytes,
                   cudaStream_t s, const pbl_peer_push* push = nullptr);
 int launch_peer_wait(const pbl_peer_push& push, cudaStream_t s);
+int launch_gptq_block(float* W, int64_t ldw, float* Err, int64_t lde, const float* Hinv, int64_t ldh, const uint8_t* mask, int64_t ldm,
+                      const float* lmean, const float* lscale, const float* hscale, const float* hzero, float maxq, int64_t N, int nc,
+                      float* losses, cudaStream_t s);
 size_t bireal_workspace_bytes(const Layer& L, int64_t M);
 size_t bireal_fixup_workspace_bytes(const Layer& L, int64_t M);
 int launch_bireal(const Layer& L, const void* x, int64_t ldx, int x_dtype, float* y, int64_t ldy, int64_t M, void* workspace,

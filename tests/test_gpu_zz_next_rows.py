@@ -69,3 +69,53 @@ def test_bireal_stream_k_and_row_group_kernels_agree():
         rc = lib.pbl_bireal_forward(p.handle, x.data_ptr(), K, 0, y_old.data_ptr(), N, M, ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
         assert rc == 0, _lib.last_error()
         assert relmax(y_new, y_old.cpu().numpy()) <= 2e-6
+
+
+# ---- GPTQ-PB calibration on the device: pb.gptq_pb against the executed reference's LowHighGPT ------------------
+@pytest.mark.parametrize("tag,gs,metric,disable", [("gptqpb_rtn_g-1_mag", -1, "magnitude", True), ("gptqpb_rtn_g128_hes", 128, "hessian", True),
+                                                   ("gptqpb_gptq_g-1_hes", -1, "hessian", False), ("gptqpb_gptq_g128_mag", 128, "magnitude", False)])
+def test_gptqpb_calibration_matches_reference_fixture(tag, gs, metric, disable, tmp_path, monkeypatch):
+    """Same inputs as oracle/gen_golden.py section 5 (the reference's own LowHighGPT, run on the CPU): weights, two calibration
+    batches, low_frac 0.9.  The mask and the quantiser tables must match; the fake-quant weights must match up to the few
+    rounding decisions that a Cholesky factor computed by another LAPACK can flip, and the packed layer built from them
+    must reproduce the reference layer's outputs."""
+    from pbllm_b200 import gptq_pb
+    from oracle.gen_golden import make_weight
+    g = load(tag)
+    N, K = 48, 256
+    W = make_weight(51, N, K, "heavy", np.float16)
+    assert np.array_equal(W, g["W"])
+    calib = make_x(52, (2, 64, K)) * (1.0 + np.arange(K, dtype=np.float32) / 64.0)
+    monkeypatch.chdir(tmp_path)
+    layer = torch.nn.Linear(K, N, bias=False).half().to(DEV)
+    layer.weight.data = t(W).clone()
+    layer.global_name = "synthetic/" + tag
+    lowq = gptq_pb.LowQuantizer(layer.weight, method="xnor", groupsize=gs)
+    highq = gptq_pb.HighQuantizer(8, True, False, False)
+    gp = gptq_pb.LowHighGPT(layer, lowq, highq, salient_metric=metric, disable_gptq=disable)
+    gp.add_batch(t(calib[0]), None)
+    gp.add_batch(t(calib[1]), None)
+    res = gp.fasterquant(0.9, blocksize=128, percdamp=0.01)
+    assert layer.weight.dtype == torch.float16 and res["error"] >= 0
+    mask = torch.load(f"outputs/mask/mask_0.9_synthetic_{tag}.pkl").cpu().numpy()
+    assert (mask == g["low_mask"]).mean() >= 0.999 and abs(mask.mean() - 0.9) < 1e-3
+    assert relmax(highq.scale.flatten(), g["high_scale"]) <= 1e-6 and np.array_equal(highq.zero.flatten().cpu().numpy(), g["high_zero"])
+    assert relmax(lowq.mean.squeeze(-1), g["low_mean"]) <= 1e-4 and relmax(lowq.scale.squeeze(-1), g["low_scale"]) <= 1e-4
+    Wq, ref = layer.weight.data.float().cpu().numpy(), g["Wq"].astype(np.float32)
+    same = (Wq == ref).mean()
+    if disable:
+        assert same >= 0.999, same                                # RTN: no error feedback, nothing to amplify
+    else:
+        assert same >= 0.97 and np.linalg.norm(Wq - ref) <= 3e-2 * np.linalg.norm(ref), (same, np.linalg.norm(Wq - ref) / np.linalg.norm(ref))
+        # calibration quality: the layer-output error on the calibration data equals the reference's to a few percent
+        X = calib.reshape(-1, K).astype(np.float64)
+        e_ours = np.linalg.norm(X @ (Wq - W.astype(np.float32)).T.astype(np.float64))
+        e_ref = np.linalg.norm(X @ (ref - W.astype(np.float32)).T.astype(np.float64))
+        assert abs(e_ours - e_ref) <= 0.05 * e_ref, (e_ours, e_ref)
+    # the calibrated layer + its mask file are exactly what replace_from_fakequant consumes
+    m = pb.PackedFakeQuantLinear.from_linear(layer, torch.load(f"outputs/mask/mask_0.9_synthetic_{tag}.pkl"), gs)
+    assert torch.equal(m.dense_weight(), layer.weight.data)
+    y = m(t(g["x"]))
+    ref_y = orc.linear(g["x"].astype(np.float32), Wq)
+    assert relmax(y, ref_y) <= 1e-3
+    assert m.packed().salient_count() <= int((~mask).sum()) + 0.01 * mask.size
