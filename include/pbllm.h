@@ -232,6 +232,13 @@ PBL_API size_t pbl_bireal_fixup_workspace(const pbl_layer* layer, int64_t M);
 PBL_API int pbl_bireal_forward_ws(const pbl_layer* layer, const void* x, int64_t ldx, int x_dtype, float* y, int64_t ldy,
                                   int64_t M, void* workspace, void* fixup_workspace, size_t fixup_workspace_bytes, void* stream);
 
+/* ---- magnitude thresholds on the device: the k-th smallest element (k 1-based, exact, NaN last -- the
+ *      semantics of torch.kthvalue, which BinaryXnorExceptOutliersLinear.gen_outlier_mask calls twice over the flattened
+ *      weight, quant/outlier_quantizer.py:58-67) by radix select; x: device, n elements of `dtype`; out: device, one element;
+ *      workspace: device, >= pbl_kth_workspace() bytes, 16 B aligned.  Stream-ordered, no host synchronisation. ---- */
+PBL_API size_t pbl_kth_workspace(void);
+PBL_API int pbl_kth_value(const void* x, int64_t n, int64_t k, int dtype, void* out, void* workspace, void* stream);
+
 /* ---- GPTQ-PB calibration: the column loop of LowHighGPT.fasterquant (gptq_pb/gptq.py:116-168) for ONE block
  *      of nc <= 128 columns, all rows, as one kernel.  W1 [N][ldw] fp32 holds the block's current weights and receives the
  *      quantised values Q1 (gptq.py:166); err_out [N][lde] receives Err1 (gptq.py:163) for the caller's cross-block update

@@ -61,6 +61,8 @@ SYMBOLS = {
     "pbl_linear_forward_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(PblPeerPush), C.c_int64, C.c_int64,
                                           C.c_void_p, C.c_size_t, C.c_void_p]),
     "pbl_peer_wait": (C.c_int, [C.POINTER(PblPeerPush), C.c_void_p]),
+    "pbl_kth_workspace": (C.c_size_t, []),
+    "pbl_kth_value": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pbl_gptq_block": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "pbl_decode_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64]),

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libpbllm.so")
-SOURCES = ["pbllm_abi.cu", "pbllm_pack.cu", "pbllm_stream.cu", "pbllm_gemv.cu", "pbllm_bireal.cu", "pbllm_decode.cu", "pbllm_gemm_tt.cu", "pbllm_gptq.cu"]
+SOURCES = ["pbllm_abi.cu", "pbllm_pack.cu", "pbllm_stream.cu", "pbllm_gemv.cu", "pbllm_bireal.cu", "pbllm_decode.cu", "pbllm_gemm_tt.cu", "pbllm_gptq.cu", "pbllm_select.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-cudart", "static",

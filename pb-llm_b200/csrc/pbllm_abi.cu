@@ -274,6 +274,18 @@ int pbl_peer_wait(const pbl_peer_push* push, void* stream) {
     return launch_peer_wait(*push, (cudaStream_t)stream);
 }
 
+size_t pbl_kth_workspace(void) { return kth_workspace_bytes(); }
+
+int pbl_kth_value(const void* x, int64_t n, int64_t k, int dtype, void* out, void* workspace, void* stream) {
+    if (!x || !out || !workspace) { set_error("pbl_kth_value: null pointer"); return PBL_ERR_NULL; }
+    if (!valid_dtype(dtype)) { set_error("pbl_kth_value: bad dtype %d", dtype); return PBL_ERR_DTYPE; }
+    if (n <= 0 || k < 1 || k > n) { set_error("pbl_kth_value: k=%lld out of range for n=%lld (selected index k out of range)", (long long)k, (long long)n); return PBL_ERR_SHAPE; }
+    if (!aligned16(workspace)) { set_error("pbl_kth_value: workspace must be 16 B aligned"); return PBL_ERR_ALIGN; }
+    int rc = device_check_impl();
+    if (rc) return rc;
+    return launch_kth_value(x, n, k, dtype, out, workspace, (cudaStream_t)stream);
+}
+
 int pbl_gptq_block(float* W1, int64_t ldw, float* err_out, int64_t lde, const float* hinv_block, int64_t ldh, const uint8_t* mask1,
                    int64_t ldm, const float* low_mean, const float* low_scale, const float* high_scale, const float* high_zero,
                    float maxq, int64_t N, int nc, float* losses, void* stream) {

@@ -88,6 +88,8 @@ int launch_peer_wait(const pbl_peer_push& push, cudaStream_t s);
 int launch_gptq_block(float* W, int64_t ldw, float* Err, int64_t lde, const float* Hinv, int64_t ldh, const uint8_t* mask, int64_t ldm,
                       const float* lmean, const float* lscale, const float* hscale, const float* hzero, float maxq, int64_t N, int nc,
                       float* losses, cudaStream_t s);
+size_t kth_workspace_bytes();
+int launch_kth_value(const void* x, int64_t n, int64_t k, int dtype, void* out, void* workspace, cudaStream_t s);
 size_t bireal_workspace_bytes(const Layer& L, int64_t M);
 size_t bireal_fixup_workspace_bytes(const Layer& L, int64_t M);
 int launch_bireal(const Layer& L, const void* x, int64_t ldx, int x_dtype, float* y, int64_t ldy, int64_t M, void* workspace,

@@ -80,6 +80,26 @@ def _free_levels(w: torch.Tensor, groupsize: int, n_pad: int, groups: int) -> to
     return out.view(-1)
 
 
+def kth_value(x: torch.Tensor, k: int) -> torch.Tensor:
+    """Exact k-th smallest element (k 1-based) of a CUDA tensor, as torch.kthvalue(x.flatten(), k)[0]: radix select in
+    libpbllm.so (pbl_kth_value), stream-ordered, no host synchronisation. Returns a 0-dim tensor of x's dtype."""
+    if not x.is_cuda or x.dtype not in _DT:
+        raise RuntimeError("kth_value needs a CUDA fp16 / bf16 / fp32 tensor")
+    xf = x.reshape(-1)
+    if xf.stride(0) != 1:
+        xf = xf.contiguous()
+    lib = _lib.load()
+    out = torch.empty((), dtype=x.dtype, device=x.device)
+    ws = torch.empty(int(lib.pbl_kth_workspace()), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.pbl_kth_value(C.c_void_p(xf.data_ptr()), xf.numel(), int(k), _DT[x.dtype], C.c_void_p(out.data_ptr()),
+                               C.c_void_p(ws.data_ptr()), _stream(x.device))
+    if rc == -3:
+        raise IndexError(_lib.last_error())         # torch.kthvalue raises IndexError for k out of range too
+    _lib.check(rc, "pbl_kth_value")
+    return out
+
+
 def pack_sizes(N: int, K: int, groupsize: int, dtype: torch.dtype) -> _lib.PblSizes:
     sz = _lib.PblSizes()
     _lib.check(_lib.load().pbl_pack_sizes(N, K, groupsize, _DT[dtype], C.byref(sz)), "pbl_pack_sizes")

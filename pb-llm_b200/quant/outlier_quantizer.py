@@ -12,6 +12,15 @@ import torch.nn as nn
 from .quantizer import _PackedBase
 
 
+def _kthvalue(w_flat, k):
+    """torch.kthvalue(w_flat, k)[0] (reference :58-66); on the device through the radix-select kernel (pbl_kth_value) --
+    the same element exactly, without the sort-sized temporary of the library call."""
+    if w_flat.is_cuda:
+        from ..packing import kth_value
+        return kth_value(w_flat, k)
+    return torch.kthvalue(w_flat, k)[0]
+
+
 def weight_quant_8bit(w, simulated=True):
     """Reference outlier_quantizer.py:10-29, per-row asymmetric 8-bit fake-quant, INCLUDING its
     behaviour for negative rows: zp = round(min) is 0 for |w| < 0.5, so negative values reach the
@@ -50,8 +59,8 @@ class BinaryXnorExceptOutliersLinear(_PackedBase):
         w = self.weight.data
         w_flat = w.reshape(-1)
         n = w_flat.numel()
-        lower_threshold = torch.kthvalue(w_flat, int(n * self.outlier_fraction / 2))[0]          # :58-62
-        upper_threshold = torch.kthvalue(w_flat, int(n * (1 - self.outlier_fraction / 2)))[0]    # :63-66
+        lower_threshold = _kthvalue(w_flat, int(n * self.outlier_fraction / 2))                  # :58-62
+        upper_threshold = _kthvalue(w_flat, int(n * (1 - self.outlier_fraction / 2)))            # :63-66
         outliers = (w < lower_threshold) | (w > upper_threshold)                                  # :69
         self.outlier_mask = outliers
         self.binary_scale = w[~self.outlier_mask].abs().mean(-1).view(-1, 1)                     # :72-74, shape [1,1]

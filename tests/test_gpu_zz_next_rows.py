@@ -119,3 +119,24 @@ def test_gptqpb_calibration_matches_reference_fixture(tag, gs, metric, disable, 
     ref_y = orc.linear(g["x"].astype(np.float32), Wq)
     assert relmax(y, ref_y) <= 1e-3
     assert m.packed().salient_count() <= int((~mask).sum()) + 0.01 * mask.size
+
+
+# ---- magnitude thresholds on the device: radix select against torch.kthvalue ------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("n", [1, 7, 1000, 4096 * 4096 + 3])
+def test_kth_value_is_torch_kthvalue(dtype, n):
+    from pbllm_b200.packing import kth_value
+    gen = torch.Generator(device=DEV).manual_seed(n)
+    x = (torch.randn(n, device=DEV, generator=gen) * 0.02).to(dtype)
+    x[::5] = x[::5].abs()
+    if n > 10:
+        x[3], x[4] = 0.0, -0.0
+    ks = sorted({1, n, max(1, n // 2), max(1, int(n * 0.05)), max(1, int(n * 0.95))})
+    for k in ks:
+        got = kth_value(x, k)
+        ref = torch.kthvalue(x.float(), k)[0]              # exact in fp32 for 16-bit inputs
+        assert got.dtype == dtype and float(got) == float(ref), (k, float(got), float(ref))
+    xv = x[1:] if n > 8 else x                              # unaligned base pointer: scalar tail path
+    assert float(kth_value(xv, 1)) == float(xv.float().min())
+    with pytest.raises(IndexError):
+        kth_value(x, n + 1)
