@@ -238,36 +238,45 @@ __global__ void __launch_bounds__(128) stream_fill_kernel(const T* __restrict__ 
 }
 
 // ---- unpack / expand: dense w_sim [rows][ldw] back from the stream -----------------------------------------------------------
-// One warp per block: levels from the sign words into a swizzled 4 KB tile (the decode kernel's tile layout), salient
-// values reconstructed over them from the entries, then the tile is written out row by row.  Entries marked as exceptions
+// One warp per block.  The 32 x 64 block is rebuilt in a row-major shared-memory tile (128-byte rows, 16-byte chunks
+// XOR-swizzled by row & 7): lane (g, t) turns its fragment-ordered sign words into the levels of its four rows x sixteen
+// columns with the decode kernel's shift trick -- ((w << rho) & 0x80008000) marks the two columns of a 32-bit word -- and
+// writes them as two 16-byte stores per row; the salient entries are reconstructed over them (value_of + k), and the tile
+// leaves as coalesced 16-byte stores (scalar stores for ragged / unaligned destinations).  Entries marked as exceptions
 // are left at their level here and overwritten by stream_exc_kernel (same stream, launched right after).
 template <typename T>
 __global__ void __launch_bounds__(128) stream_unpack_kernel(const uint2* __restrict__ fsign, const uint32_t* __restrict__ eptr,
                                                             const uint32_t* __restrict__ ent, const float2* __restrict__ affine,
                                                             int64_t n_rows, int64_t n_cols, int tiles_c, int64_t groups,
                                                             int tiles_per_group, uint32_t nblocks, T* __restrict__ out, int64_t ldw) {
-    __shared__ __align__(16) uint16_t tiles[4][kRgRows * kTileCols];
+    __shared__ __align__(16) uint8_t tiles[4][kRgRows * kTileCols * 2];
     __shared__ float2 affs[4][kRgRows];
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const uint32_t blk = blockIdx.x * 4u + wid;
     if (blk >= nblocks) return;
-    uint16_t* tile = tiles[wid];
+    uint8_t* tile = tiles[wid];
     const uint32_t rg = blk / (uint32_t)tiles_c, kb = blk - rg * (uint32_t)tiles_c;
     const uint32_t g = lane >> 2, t = lane & 3u;
     const uint2 sg = fsign[(size_t)blk * kRgRows + lane];
     affs[wid][lane] = affine[((int64_t)rg * kRgRows + lane) * groups + kb / tiles_per_group];
     __syncwarp();
-#pragma unroll 1
+    auto phys = [](uint32_t r, uint32_t c) { return r * 128u + ((((c >> 3) ^ r) & 7u) << 4) + (c & 7u) * 2u; };   // byte offset of (r, c)
+#pragma unroll
     for (uint32_t j = 0; j < 4; ++j) {
         const uint32_t r = g + 8u * j;
         const float2 a = affs[wid][r];
-        const uint16_t lo = (uint16_t)bits_of<T>(from_f32<T>(a.x)), hi = (uint16_t)bits_of<T>(from_f32<T>(a.y));
+        const uint32_t lo = bits_of<T>(from_f32<T>(a.x)), hi = bits_of<T>(from_f32<T>(a.y));
+        const uint32_t HH = hi * 0x10001u, DD = (lo ^ hi) * 0x10001u;
         const uint32_t wd = (j >> 1) ? sg.y : sg.x;
-        for (uint32_t o = 0; o < 16; ++o) {
-            const uint32_t q = o >> 2, hi2 = (o >> 1) & 1u, e = o & 1u;
-            const uint32_t pos = (15u - (4u * q + (j & 1u) + 2u * hi2)) + 16u * e;
-            tile[st::tile_slot(r, 16u * t + o)] = ((wd >> pos) & 1u) ? lo : hi;
+        uint32_t v[8];
+#pragma unroll
+        for (uint32_t w = 0; w < 8; ++w) {                    // word w = columns 16t + 2w, 2w+1: fragment register rho of the decode kernel
+            const uint32_t rho = 4u * (w >> 1) + (j & 1u) + 2u * (w & 1u);
+            const uint32_t m = ((wd << rho) >> 15) & 0x00010001u;          // bit 1 = LOW level
+            v[w] = HH ^ (DD & (m * 0xFFFFu));
         }
+        *reinterpret_cast<uint4*>(tile + phys(r, 16u * t)) = make_uint4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<uint4*>(tile + phys(r, 16u * t + 8u)) = make_uint4(v[4], v[5], v[6], v[7]);
     }
     __syncwarp();
     // salient values over the levels (padding copies of an entry rewrite the same value: no hazard)
@@ -276,19 +285,32 @@ __global__ void __launch_bounds__(128) stream_unpack_kernel(const uint2* __restr
         const uint32_t e = ent[i];
         const int k = st::entry_k(e);
         if (k == -8) continue;
-        const uint32_t slot = st::entry_slot(e);
-        const float2 a = affs[wid][slot >> 6];
-        tile[slot] = (uint16_t)st::unord16(st::ord16(value_of<T>(e & 0xFFFFu, a.x, a.y)) + k);
+        uint32_t r, c;
+        st::slot_pos(st::entry_slot(e), r, c);
+        const float2 a = affs[wid][r];
+        *reinterpret_cast<uint16_t*>(tile + phys(r, c)) = (uint16_t)st::unord16(st::ord16(value_of<T>(e & 0xFFFFu, a.x, a.y)) + k);
     }
     __syncwarp();
     const int64_t row0 = (int64_t)rg * kRgRows, col0 = (int64_t)kb * kTileCols;
-    for (uint32_t r = 0; r < (uint32_t)kRgRows; ++r) {
-        const int64_t row = row0 + r;
-        if (row >= n_rows) break;
+    const bool fast = row0 + kRgRows <= n_rows && col0 + kTileCols <= n_cols && (ldw & 7) == 0 &&
+                      (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+    if (fast) {                                               // 4 rows x 8 chunks of 16 bytes per pass
+        const uint32_t rl = lane >> 3, ch = lane & 7u;
 #pragma unroll
-        for (uint32_t h = 0; h < 2; ++h) {
-            const uint32_t c = h * 32u + lane;
-            if (col0 + c < n_cols) out[row * ldw + col0 + c] = of_bits<T>(tile[st::tile_slot(r, c)]);
+        for (uint32_t r4 = 0; r4 < (uint32_t)kRgRows; r4 += 4) {
+            const uint32_t r = r4 + rl;
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + r * 128u + (((ch ^ r) & 7u) << 4));
+            *reinterpret_cast<uint4*>(out + (row0 + r) * ldw + col0 + ch * 8u) = v;
+        }
+    } else {
+        for (uint32_t r = 0; r < (uint32_t)kRgRows; ++r) {
+            const int64_t row = row0 + r;
+            if (row >= n_rows) break;
+#pragma unroll
+            for (uint32_t h = 0; h < 2; ++h) {
+                const uint32_t c = h * 32u + lane;
+                if (col0 + c < n_cols) out[row * ldw + col0 + c] = of_bits<T>(*reinterpret_cast<const uint16_t*>(tile + phys(r, c)));
+            }
         }
     }
 }
