@@ -29,10 +29,10 @@ static_assert(kSmemBytes <= 232448, "exceeds 227 KB");
 }  // namespace tt
 
 // Tile rasterisation: n-tiles are taken in groups of kGroupN; inside a group the tile index runs n-fastest, so
-// the ~74 pair tiles in flight share one 8 x 256-row weight slab (<= 17 MB at K = 4096) and a few token tiles:
+// the ~74 pair tiles in flight share one 16 x 256-row weight slab (<= 34 MB at K = 4096) and a few token tiles:
 // the slab stays in L2 across the group's waves instead of the whole scratch (90 MB for 11008 x 4096) being
 // re-fetched from HBM every wave.
-constexpr int kGroupN = 8;
+constexpr int kGroupN = 16;
 __device__ __forceinline__ void tile_mn(int t, const GemmParams& p, int& m_tile, int& n_tile) {
     const int per_group = kGroupN * p.m_tiles;
     const int g = t / per_group, r = t - g * per_group;
