@@ -143,6 +143,13 @@ __device__ __forceinline__ uint4 dk_lds128(uint32_t a) {
     return v;
 }
 
+// one lane of the (converged) warp
+__device__ __forceinline__ bool dk_elect() {
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(r));
+    return r != 0u;
+}
+
 __device__ __forceinline__ unsigned long long dk_now() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -161,11 +168,167 @@ __device__ __forceinline__ void st_release_sys(uint32_t* a, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a), "r"(v) : "memory");
 }
 
+// Which of a CTA's row groups are shared with other CTAs, and how: {rg_a, rg_b, head split?, slot, expected, tail split?,
+// slot, expected}.  Units are what the kernel deals out to its warps (blocks, or pairs of blocks): the CTA owns units
+// [c_lo, c_hi), a row group has TC of them, warp gw of the grid owns q (+1 for the first rem warps).
+__device__ __forceinline__ void dk_meta(uint32_t* s_meta, uint32_t c_lo, uint32_t c_hi, uint32_t TC, uint32_t q, uint32_t rem) {
+    constexpr uint32_t kWarps = dk::kWarps;
+    const uint32_t rg_a = c_lo / TC, rg_b = (c_hi - 1u) / TC;
+    auto owner = [&](uint32_t b) {            // CTA whose run contains block b
+        const uint32_t cut = rem * (q + 1u);
+        const uint32_t gw = b < cut ? b / (q + 1u) : rem + (b - cut) / q;
+        return gw / kWarps;
+    };
+    s_meta[0] = rg_a; s_meta[1] = rg_b;
+    const bool hs = c_lo > rg_a * TC || c_hi < rg_a * TC + TC;
+    const bool ts = rg_b != rg_a && c_hi < rg_b * TC + TC;
+    s_meta[2] = hs; s_meta[5] = ts;
+    if (hs) { const uint32_t f = owner(rg_a * TC); s_meta[3] = blockIdx.x - f; s_meta[4] = owner(rg_a * TC + TC - 1u) - f + 1u; }
+    if (ts) { const uint32_t f = owner(rg_b * TC); s_meta[6] = blockIdx.x - f; s_meta[7] = owner(rg_b * TC + TC - 1u) - f + 1u; }
+}
+
+// The end of a decode kernel, shared by its variants: cross-warp reduction in shared memory; row groups shared with other
+// CTAs go through the workspace.  Warp w's region starts at smem + w * kWarpStride: its tail partial at offset 0 (aliasing
+// the tile), its head partial at kHeadOff, both fp32 [token][row].
+template <typename T, int kNT, bool kPush, bool kTrace, int kWarpStride, int kHeadOff>
+__device__ __forceinline__ void dk_finish(const dk::Params& p, uint8_t* smem, const uint32_t* s_hrg, const uint32_t* s_trg,
+                                          const uint32_t* s_meta, const uint32_t c_lo, const uint32_t c_hi, const int m0,
+                                          unsigned long long (&tr)[8], const uint32_t my_units) {
+    using namespace dk;
+    constexpr int kOutP = kOut * kNT;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    // ---- cross-warp reduction in shared memory; row groups shared with other CTAs go through the workspace ----------
+    if (kTrace) tr[3] = dk_now();
+    __syncthreads();
+    if (kTrace) tr[4] = dk_now();
+    auto trace_out = [&]() {
+        if (kTrace && lane == 0) {
+            tr[6] = dk_now();
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            tr[7] = ((unsigned long long)smid << 32) | my_units;
+            unsigned long long* o = p.trace + ((size_t)blockIdx.x * kWarps + wid) * 8u;
+            for (int i = 0; i < 8; ++i) o[i] = tr[i];
+        }
+    };
+    // kPush: when every warp that stores outputs (warps 0 and 1 of every CTA, below; the loop's stores are ordered before
+    // them by the barrier above) has passed its system-scope fence, the last one publishes the new epoch to every rank.
+    auto publish = [&]() {
+        if constexpr (kPush) {
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_system();
+                const uint32_t total = 2u * gridDim.x * gridDim.y;
+                if (atomicAdd(p.sync_ctr, 1u) == total - 1u) {
+                    p.sync_ctr[0] = 0u;
+                    const uint32_t epoch = p.sync_ctr[1] + 1u;
+                    p.sync_ctr[1] = epoch;
+                    __threadfence_system();
+                    for (uint32_t d = 0; d < p.n_dst; ++d) st_release_sys(p.flag_dst[d] + p.rank, epoch);
+                }
+            }
+        }
+    };
+    // Two warps finish the CTA: thread t < 64 owns four consecutive outputs per token group -- token 8u + (t>>3), rows
+    // 4*(t&7)..+3 of the row group, i.e. float4 number 64u + t of every [token][row] partial buffer -- so each partial costs
+    // one LDS.128 per thread and group.
+    if (tid >= 64u) { if (kTrace) tr[5] = tr[4]; trace_out(); return; }
+    if (c_lo >= c_hi) { publish(); return; }
+    const uint32_t rg_a = s_meta[0], rg_b = s_meta[1];
+    const uint32_t om = tid >> 3, or4 = (tid & 7u) * 4u;
+    uint32_t hrg[kWarps], trg[kWarps];
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) { hrg[w] = s_hrg[w]; trg[w] = s_trg[w]; }
+    const bool hs = s_meta[2] != 0u, ts = s_meta[5] != 0u;
+#pragma unroll
+    for (int u = 0; u < kNT; ++u) {                          // one round per token group: float4 number 64u + t of the buffers
+        const int64_t yoff = (int64_t)(m0 + kTok * u + om) * p.ldy;
+        const bool tok_ok = (m0 + kTok * u + (int)om) < p.M;
+        auto emit = [&](uint32_t r, const float4 v) {            // + bias, round, store the four outputs of row group r
+            const int orow = (int)(r * kRgRows + or4);
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+            if (tok_ok) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (orow + j < p.N) {
+                        const T o = from_f32<T>((p.bias ? p.bias[orow + j] : 0.f) + vv[j]);
+                        if constexpr (kPush) {
+                            for (uint32_t d = 0; d < p.n_dst; ++d) (reinterpret_cast<T*>(p.y_dst[d]) + yoff)[orow + j] = o;
+                        } else {
+                            (reinterpret_cast<T*>(p.y) + yoff)[orow + j] = o;
+                        }
+                    }
+            }
+        };
+        float4 v_split[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};   // head / tail row group (when shared)
+        for (uint32_t r = rg_a; r <= rg_b; ++r) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool any = false;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {                   // fixed order: warp 0's partial first
+                if (hrg[w] == r) {
+                    const float4 a4 = reinterpret_cast<const float4*>(smem + w * kWarpStride + kHeadOff)[64 * u + tid];
+                    v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w; any = true;
+                }
+                if (trg[w] == r) {
+                    const float4 a4 = reinterpret_cast<const float4*>(smem + w * kWarpStride)[64 * u + tid];
+                    v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w; any = true;
+                }
+            }
+            if (!any) continue;                                  // stored by the single warp that owned it
+            const bool split = (r == rg_a && s_meta[2]) || (r == rg_b && s_meta[5]);
+            if (!split) emit(r, v);                              // the whole row group lives in this CTA
+            else if (r == rg_a) v_split[0] = v;
+            else v_split[1] = v;
+        }
+        if (kTrace) tr[5] = dk_now();
+        if (!hs && !ts) continue;
+        // Row groups shared with other CTAs.  Every contributor but the last parks its partial in its own slot as 64-bit
+        // stores {value, valid tag}: data and flag travel together, so there is no fence, no counter and no barrier.  The
+        // last contributor (highest CTA index, so everything it waits for was scheduled before it) polls the slots, sums them
+        // in CTA order (deterministic), clears them for the next kernel, and writes y.
+        unsigned long long* ws = reinterpret_cast<unsigned long long*>(p.ws_part);
+#pragma unroll
+        for (int f = 1; f >= 0; --f) {                           // the tail group first: this CTA is never its last contributor
+            if (!(f == 0 ? hs : ts)) continue;
+            const uint32_t r = f == 0 ? rg_a : rg_b, slot = s_meta[f == 0 ? 3 : 6], expected = s_meta[f == 0 ? 4 : 7];
+            unsigned long long* part = ws + (((size_t)blockIdx.y * p.rgs + r) * p.slots) * kOutP + kOut * u + tid * 4u;
+            const float4 v = v_split[f];
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+            if (slot + 1u < expected) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned long long w64 = (1ull << 32) | (unsigned long long)__float_as_uint(vv[j]);
+                    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(part + (size_t)slot * kOutP + j), "l"(w64) : "memory");
+                }
+            } else {
+                float sum[4] = {0.f, 0.f, 0.f, 0.f};
+                for (uint32_t k = 0; k + 1u < expected; ++k) {
+                    unsigned long long w64[4];
+                    do {                                         // four independent loads in flight per poll
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w64[j]) : "l"(part + (size_t)k * kOutP + j) : "memory");
+                    } while (((w64[0] & w64[1] & w64[2] & w64[3]) >> 32) == 0ull);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        sum[j] += __uint_as_float((uint32_t)w64[j]);
+                        asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(part + (size_t)k * kOutP + j), "l"(0ull) : "memory");
+                    }
+                }
+                emit(r, make_float4(sum[0] + vv[0], sum[1] + vv[1], sum[2] + vv[2], sum[3] + vv[3]));
+            }
+        }
+    }
+    publish();
+    trace_out();
+}
+
 template <typename T, int kOcc, bool kTrace = false, int kNT = 1, bool kLean = false, bool kPush = false>
 __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk::Params p) {
     using namespace dk;
     constexpr int kWarpBytes = dk::kWarpBytes + (kNT - 1) * kHeadBytes;
-    constexpr int kTokP = kTok * kNT, kOutP = kOut * kNT;
+    constexpr int kTokP = kTok * kNT;
     constexpr uint32_t kOne2 = dk_one2<T>();
     unsigned long long tr[8];
     if (kTrace) { tr[0] = dk_now(); }
@@ -237,20 +400,7 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
     if (w_lo < w_hi) load_levels(rg, cur_g);
 
     if (lane == 0) { s_hrg[wid] = kNone; s_trg[wid] = kNone; }
-    if (tid == 0) {                               // which of this CTA's row groups are shared with other CTAs, and how
-        const uint32_t rg_a = c_lo / TC, rg_b = (c_hi - 1u) / TC;
-        auto owner = [&](uint32_t b) {            // CTA whose run contains block b
-            const uint32_t cut = rem * (q + 1u);
-            const uint32_t gw = b < cut ? b / (q + 1u) : rem + (b - cut) / q;
-            return gw / kWarps;
-        };
-        s_meta[0] = rg_a; s_meta[1] = rg_b;
-        const bool hs = c_lo > rg_a * TC || c_hi < rg_a * TC + TC;
-        const bool ts = rg_b != rg_a && c_hi < rg_b * TC + TC;
-        s_meta[2] = hs; s_meta[5] = ts;
-        if (hs) { const uint32_t f = owner(rg_a * TC); s_meta[3] = blockIdx.x - f; s_meta[4] = owner(rg_a * TC + TC - 1u) - f + 1u; }
-        if (ts) { const uint32_t f = owner(rg_b * TC); s_meta[6] = blockIdx.x - f; s_meta[7] = owner(rg_b * TC + TC - 1u) - f + 1u; }
-    }
+    if (tid == 0) dk_meta(s_meta, c_lo, c_hi, TC, q, rem);
 
     uint32_t ci = 0;                               // index of the current block in the eptr register chunk
     uint32_t cs = 0, cph = 0;                      // ring stage of the current block and the parity its mbarrier completes with
@@ -511,131 +661,310 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
         if (blk + 1u < w_hi) do_block(blk + 1u, X1, X0);
     }
 
-    // ---- cross-warp reduction in shared memory; row groups shared with other CTAs go through the workspace ----------
-    if (kTrace) tr[3] = dk_now();
-    __syncthreads();
-    if (kTrace) tr[4] = dk_now();
-    auto trace_out = [&]() {
-        if (kTrace && lane == 0) {
-            tr[6] = dk_now();
-            uint32_t smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            tr[7] = ((unsigned long long)smid << 32) | (w_hi - w_lo);
-            unsigned long long* o = p.trace + ((size_t)blockIdx.x * kWarps + wid) * 8u;
-            for (int i = 0; i < 8; ++i) o[i] = tr[i];
+    dk_finish<T, kNT, kPush, kTrace, kWarpBytes, kTileBytes>(p, smem, s_hrg, s_trg, s_meta, c_lo, c_hi, m0, tr, w_hi - w_lo);
+}
+
+// ---- the pair kernel: the common case (one group per row, K a multiple of 128, M <= 8, aligned activations) -----------
+//
+// Same layout, same arithmetic, same stream-K partition and end of kernel as decode_mma_kernel, but the unit of work is a
+// PAIR of k-adjacent blocks (32 rows x 128 columns): per-block bookkeeping is what bounded the kernel above (a warp spends
+// about 1 us per block on one serial chain wait -> patch -> barrier -> ldmatrix/MMA -> barrier -> reset -> barrier with ~250
+// issued instructions, profiles/r02_decode_ablation.md), so here
+//   * one ring stage, one mbarrier wait, one pair of bulk copies, one activation prefetch and three warp barriers serve two
+//     blocks; the warp's tile is 8 KB (block A | block B), its entries patched in one go;
+//   * the sixteen MMAs of a pair run on four independent accumulator chains (block x row half) instead of two;
+//   * everything rare (groups, ragged K, unaligned activations, 9..16 tokens) stays in the general kernel, so the loop
+//     has no branches for it.
+namespace dk2 {
+constexpr int kWarps = dk::kWarps, kThreads = dk::kThreads, kTok = dk::kTok;
+constexpr int kTileBytes = 2 * dk::kTileBytes;            // 8192: block A of the pair at 0, block B at 4096
+constexpr int kHeadBytes = dk::kHeadBytes;
+constexpr int kStages = 2;                                // pairs in flight per warp (= 4 blocks)
+constexpr int kEntCap = 112;                              // 16-byte entry units of a pair held by a ring stage (the rest: global)
+constexpr int kStageBytes = 512 + kEntCap * 16;           // 2304
+constexpr int kWarpBytes = kTileBytes + kHeadBytes + kStages * kStageBytes + 128;   // 13952: + mbarriers, padded to 128
+constexpr int kUnitsPerLane = (kEntCap + 31) / 32;        // 4 entry units per lane and pair
+static_assert(kWarpBytes % 128 == 0, "per-warp regions must keep the tile 128-byte aligned");
+}  // namespace dk2
+
+template <typename T, bool kTrace = false, bool kPush = false>
+__global__ void __launch_bounds__(dk2::kThreads, 2) decode_pair_kernel(const dk::Params p) {
+    using namespace dk2;
+    using dk::kOut;
+    constexpr uint32_t kOne2 = dk_one2<T>();
+    constexpr uint32_t kNone = 0xffffffffu;
+    unsigned long long tr[8];
+    if (kTrace) { tr[0] = dk_now(); }
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint32_t s_hrg[kWarps], s_trg[kWarps];
+    __shared__ uint32_t s_meta[8];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    uint8_t* wsm = smem + wid * kWarpBytes;
+    const uint32_t tile_s = smem_u32(wsm);
+    float* head_red = reinterpret_cast<float*>(wsm + kTileBytes);
+    float* tail_red = reinterpret_cast<float*>(wsm);      // aliases the tile: written only when the tile is at rest
+
+    // ---- work partition, in pairs: warp gw owns pairs [gw*q + min(gw,rem), ...) --------------------------------------
+    const uint32_t TCp = p.tiles_c >> 1, q = p.q, rem = p.rem;
+    auto wstart = [&](uint32_t gw) { return gw * q + min(gw, rem); };
+    const uint32_t gw0 = blockIdx.x * kWarps;
+    const uint32_t c_lo = wstart(gw0), c_hi = wstart(gw0 + kWarps);
+    const uint32_t w_lo = wstart(gw0 + wid), w_hi = wstart(gw0 + wid + 1u);
+    const int m0 = blockIdx.y * kTok;
+
+    // entry offsets first (the bulk copies below depend on them: the one DRAM round trip before any weight byte moves):
+    // lane l holds eptr[2 * chunk + l], i.e. the three offsets of pair chunk + j sit in lanes 2j, 2j+1, 2j+2; a chunk serves
+    // 13 pairs (the refill two pairs ahead reads lanes up to 2j + 6)
+    uint32_t epr = 0;
+    if (w_lo < w_hi && 2u * w_lo + lane <= 2u * w_hi) epr = __ldg(p.eptr + 2u * w_lo + lane);
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sts_v4(tile_s + lane * 16u + (uint32_t)i * 512u, kOne2, kOne2, kOne2, kOne2);
+
+    const uint32_t ring_s = tile_s + kTileBytes + kHeadBytes, bar_s = ring_s + kStages * kStageBytes;
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < kStages; ++st) mbar_init(bar_s + 8u * st, 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    auto issue = [&](uint32_t pr, uint32_t st, uint32_t eb, uint32_t n) {       // lane 0: one pair = 512 B of sign words + its entries
+        const uint32_t n1 = min(n, (uint32_t)kEntCap), dst = ring_s + st * kStageBytes, bar = bar_s + 8u * st;
+        mbar_arrive_expect_tx(bar, 512u + n1 * 16u);
+        dk_bulk_g2s(dst, p.fsign + (size_t)pr * (2u * kRgRows), 512u, bar);
+        if (n1) dk_bulk_g2s(dst + 512u, p.ent + eb, n1 * 16u, bar);
+    };
+#pragma unroll
+    for (int st = 0; st < kStages; ++st) {
+        const uint32_t eb = __shfl_sync(0xffffffffu, epr, 2 * st), n = __shfl_sync(0xffffffffu, epr, 2 * st + 2) - eb;
+        if (w_lo + st < w_hi) { if (dk_elect()) issue(w_lo + st, st, eb, n); }
+    }
+    uint32_t rg = 0, kp = 0;
+    if (w_lo < w_hi) { rg = w_lo / TCp; kp = w_lo - rg * TCp; }
+    const uint32_t rg_first = rg;
+    const bool has_mid = p.has_mid != 0u;
+    const uint32_t g4 = lane >> 2, t4 = lane & 3u;
+    float2 lv[4];                                   // {lo, hi} of this lane's four accumulator rows of the current row group
+    auto load_levels = [&](uint32_t rgi) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) lv[j] = __ldg(p.affine + (size_t)(rgi * kRgRows + g4 + 8u * j));
+    };
+#pragma unroll
+    for (int j = 0; j < 4; ++j) lv[j] = make_float2(0.f, 0.f);
+    if (w_lo < w_hi) load_levels(rg);
+
+    if (lane == 0) { s_hrg[wid] = kNone; s_trg[wid] = kNone; }
+    if (tid == 0) dk_meta(s_meta, c_lo, c_hi, TCp, q, rem);
+
+    // activations: lane -> (token lane>>2, 16-column segment lane&3) of each of the pair's two 8 x 64 blocks
+    const uint32_t xtok = lane >> 2, xseg = lane & 3u;
+    const bool x_tok_ok = (m0 + (int)xtok) < p.M;
+    uint32_t xoff_row = (uint32_t)(((int64_t)(m0 + (x_tok_ok ? (int)xtok : 0)) * p.ldx + 16 * xseg) * 2);
+    asm volatile("" : "+r"(xoff_row));
+    uint32_t xoff = xoff_row + kp * (2u * kTileCols * 2u);      // loop-carried: byte offset of the next pair to load
+    uint32_t xkp = kp;
+    const uint8_t* xbytes = reinterpret_cast<const uint8_t*>(p.x);
+    struct XF { uint32_t a[8], b[8]; };                   // B fragments of block A / block B
+    auto load_x_next = [&](XF& X) {
+        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(X.a[0]), "=r"(X.a[1]), "=r"(X.a[2]), "=r"(X.a[3]), "=r"(X.a[4]), "=r"(X.a[5]), "=r"(X.a[6]), "=r"(X.a[7])
+                     : "l"(xbytes + xoff));
+        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(X.b[0]), "=r"(X.b[1]), "=r"(X.b[2]), "=r"(X.b[3]), "=r"(X.b[4]), "=r"(X.b[5]), "=r"(X.b[6]), "=r"(X.b[7])
+                     : "l"(xbytes + xoff + kTileCols * 2u));
+        ++xkp;
+        const bool wrap = xkp == TCp;
+        xkp = wrap ? 0u : xkp;
+        xoff = wrap ? xoff_row : xoff + 2u * kTileCols * 2u;
+    };
+
+    const uint32_t lm_row = (lane & 7u) + ((lane >> 3) & 1u) * 8u;
+    const uint32_t lm_base0 = tile_s + lm_row * 128u + (((lane >> 4) ^ (lm_row & 7u)) << 4);
+    uint32_t lm_q[4];
+#pragma unroll
+    for (int qi = 0; qi < 4; ++qi) {
+        lm_q[qi] = lm_base0 ^ ((uint32_t)qi << 5);
+        asm volatile("" : "+r"(lm_q[qi]));
+    }
+
+    // accumulators in the mma C layout: acc_d[block of the pair][row half][4], acc_x the sum of x, acc the folded result
+    float acc[2][4], acc_d[2][2][4], acc_x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        acc[0][i] = acc[1][i] = acc_x[i] = 0.f;
+        acc_d[0][0][i] = acc_d[0][1][i] = acc_d[1][0][i] = acc_d[1][1][i] = 0.f;
+    }
+    auto fold = [&]() {
+        float mid[4], half[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { mid[j] = 0.5f * (lv[j].x + lv[j].y); half[j] = 0.5f * (lv[j].y - lv[j].x); }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = 2 * h + (i >> 1);
+                acc[h][i] = fmaf(half[j], acc_d[0][h][i] + acc_d[1][h][i], acc[h][i]);
+                if (has_mid) acc[h][i] = fmaf(mid[j], acc_x[i & 1], acc[h][i]);
+                acc_d[0][h][i] = acc_d[1][h][i] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc_x[i] = 0.f;
+    };
+    auto store_frag = [&](float* dst) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t r = 16u * h + g4;
+            dst[(2u * t4) * kRgRows + r] = acc[h][0];
+            dst[(2u * t4 + 1u) * kRgRows + r] = acc[h][1];
+            dst[(2u * t4) * kRgRows + r + 8u] = acc[h][2];
+            dst[(2u * t4 + 1u) * kRgRows + r + 8u] = acc[h][3];
         }
     };
-    // kPush: when every warp that stores outputs (warps 0 and 1 of every CTA, below; the loop's stores are ordered before
-    // them by the barrier above) has passed its system-scope fence, the last one publishes the new epoch to every rank.
-    auto publish = [&]() {
-        if constexpr (kPush) {
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_system();
-                const uint32_t total = 2u * gridDim.x * gridDim.y;
-                if (atomicAdd(p.sync_ctr, 1u) == total - 1u) {
-                    p.sync_ctr[0] = 0u;
-                    const uint32_t epoch = p.sync_ctr[1] + 1u;
-                    p.sync_ctr[1] = epoch;
-                    __threadfence_system();
-                    for (uint32_t d = 0; d < p.n_dst; ++d) st_release_sys(p.flag_dst[d] + p.rank, epoch);
-                }
+
+    if (kTrace) tr[1] = dk_now();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (kTrace) tr[2] = dk_now();
+    if constexpr (kPush) {
+        if (p.wait_prev) {
+            if (tid < p.n_dst) {
+                const uint32_t want = p.sync_ctr[1];
+                while ((int32_t)(ld_acquire_sys(p.flag_local + tid) - want) < 0) { }
             }
-        }
-    };
-    // Two warps finish the CTA: thread t < 64 owns four consecutive outputs per token group -- token 8u + (t>>3), rows
-    // 4*(t&7)..+3 of the row group, i.e. float4 number 64u + t of every [token][row] partial buffer -- so each partial costs
-    // one LDS.128 per thread and group.
-    if (tid >= 64u) { if (kTrace) tr[5] = tr[4]; trace_out(); return; }
-    if (c_lo >= c_hi) { publish(); return; }
-    const uint32_t rg_a = s_meta[0], rg_b = s_meta[1];
-    const uint32_t om = tid >> 3, or4 = (tid & 7u) * 4u;
-    uint32_t hrg[kWarps], trg[kWarps];
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) { hrg[w] = s_hrg[w]; trg[w] = s_trg[w]; }
-    const bool hs = s_meta[2] != 0u, ts = s_meta[5] != 0u;
-#pragma unroll
-    for (int u = 0; u < kNT; ++u) {                          // one round per token group: float4 number 64u + t of the buffers
-        const int64_t yoff = (int64_t)(m0 + kTok * u + om) * p.ldy;
-        const bool tok_ok = (m0 + kTok * u + (int)om) < p.M;
-        auto emit = [&](uint32_t r, const float4 v) {            // + bias, round, store the four outputs of row group r
-            const int orow = (int)(r * kRgRows + or4);
-            const float vv[4] = {v.x, v.y, v.z, v.w};
-            if (tok_ok) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (orow + j < p.N) {
-                        const T o = from_f32<T>((p.bias ? p.bias[orow + j] : 0.f) + vv[j]);
-                        if constexpr (kPush) {
-                            for (uint32_t d = 0; d < p.n_dst; ++d) (reinterpret_cast<T*>(p.y_dst[d]) + yoff)[orow + j] = o;
-                        } else {
-                            (reinterpret_cast<T*>(p.y) + yoff)[orow + j] = o;
-                        }
-                    }
-            }
-        };
-        float4 v_split[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};   // head / tail row group (when shared)
-        for (uint32_t r = rg_a; r <= rg_b; ++r) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            bool any = false;
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w) {                   // fixed order: warp 0's partial first
-                if (hrg[w] == r) {
-                    const float4 a4 = reinterpret_cast<const float4*>(smem + w * kWarpBytes + kTileBytes)[64 * u + tid];
-                    v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w; any = true;
-                }
-                if (trg[w] == r) {
-                    const float4 a4 = reinterpret_cast<const float4*>(smem + w * kWarpBytes)[64 * u + tid];
-                    v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w; any = true;
-                }
-            }
-            if (!any) continue;                                  // stored by the single warp that owned it
-            const bool split = (r == rg_a && s_meta[2]) || (r == rg_b && s_meta[5]);
-            if (!split) emit(r, v);                              // the whole row group lives in this CTA
-            else if (r == rg_a) v_split[0] = v;
-            else v_split[1] = v;
-        }
-        if (kTrace) tr[5] = dk_now();
-        if (!hs && !ts) continue;
-        // Row groups shared with other CTAs.  Every contributor but the last parks its partial in its own slot as 64-bit
-        // stores {value, valid tag}: data and flag travel together, so there is no fence, no counter and no barrier.  The
-        // last contributor (highest CTA index, so everything it waits for was scheduled before it) polls the slots, sums them
-        // in CTA order (deterministic), clears them for the next kernel, and writes y.
-        unsigned long long* ws = reinterpret_cast<unsigned long long*>(p.ws_part);
-#pragma unroll
-        for (int f = 1; f >= 0; --f) {                           // the tail group first: this CTA is never its last contributor
-            if (!(f == 0 ? hs : ts)) continue;
-            const uint32_t r = f == 0 ? rg_a : rg_b, slot = s_meta[f == 0 ? 3 : 6], expected = s_meta[f == 0 ? 4 : 7];
-            unsigned long long* part = ws + (((size_t)blockIdx.y * p.rgs + r) * p.slots) * kOutP + kOut * u + tid * 4u;
-            const float4 v = v_split[f];
-            const float vv[4] = {v.x, v.y, v.z, v.w};
-            if (slot + 1u < expected) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const unsigned long long w64 = (1ull << 32) | (unsigned long long)__float_as_uint(vv[j]);
-                    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(part + (size_t)slot * kOutP + j), "l"(w64) : "memory");
-                }
-            } else {
-                float sum[4] = {0.f, 0.f, 0.f, 0.f};
-                for (uint32_t k = 0; k + 1u < expected; ++k) {
-                    unsigned long long w64[4];
-                    do {                                         // four independent loads in flight per poll
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w64[j]) : "l"(part + (size_t)k * kOutP + j) : "memory");
-                    } while (((w64[0] & w64[1] & w64[2] & w64[3]) >> 32) == 0ull);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        sum[j] += __uint_as_float((uint32_t)w64[j]);
-                        asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(part + (size_t)k * kOutP + j), "l"(0ull) : "memory");
-                    }
-                }
-                emit(r, make_float4(sum[0] + vv[0], sum[1] + vv[1], sum[2] + vv[2], sum[3] + vv[3]));
-            }
+            __syncthreads();
         }
     }
-    publish();
-    trace_out();
+    XF X0, X1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) X0.a[i] = X0.b[i] = X1.a[i] = X1.b[i] = 0u;
+    if (w_lo < w_hi) load_x_next(X0);
+    __syncwarp();
+
+    uint32_t ci = 0;                               // pair index inside the eptr chunk
+    uint32_t cs = 0, cph = 0;                      // ring stage of the current pair and its mbarrier parity
+    const uint16_t one16 = (uint16_t)kOne2;
+    auto do_pair = [&](const uint32_t pr, const XF& X, XF& Xn) {
+        const bool more = pr + 1u < w_hi;
+        if (more) load_x_next(Xn);
+        if (ci > 12u) {                                 // rare: a run longer than 13 pairs refills the offsets
+            if (2u * pr + lane <= 2u * w_hi) epr = __ldg(p.eptr + 2u * pr + lane);
+            ci = 0;
+        }
+        const uint32_t eb = __shfl_sync(0xffffffffu, epr, 2u * ci);
+        const uint32_t nA = __shfl_sync(0xffffffffu, epr, 2u * ci + 1u) - eb, n = __shfl_sync(0xffffffffu, epr, 2u * ci + 2u) - eb;
+        const uint32_t stage = ring_s + cs * kStageBytes;
+
+        mbar_wait(bar_s + 8u * cs, cph);
+        const uint2 sgA = dk_lds64(stage + lane * 8u), sgB = dk_lds64(stage + 256u + lane * 8u);
+        const uint32_t n1 = min(n, (uint32_t)kEntCap);
+        uint32_t ad[kUnitsPerLane][4];                  // where this lane's entries went: the reset needs no arithmetic
+#pragma unroll
+        for (int j = 0; j < kUnitsPerLane; ++j) {       // entry unit lane + 32 j of the pair: block A's units first, then block B's
+            const uint32_t i = lane + 32u * j;
+            const uint32_t tb = tile_s + (i >= nA ? (uint32_t)dk::kTileBytes : 0u);
+            ad[j][0] = ad[j][1] = ad[j][2] = ad[j][3] = tb;
+            if (i < n1) {
+                const uint4 e = dk_lds128(stage + 512u + i * 16u);
+                ad[j][0] = tb + (e.x >> 20); ad[j][1] = tb + (e.y >> 20); ad[j][2] = tb + (e.z >> 20); ad[j][3] = tb + (e.w >> 20);
+                sts_u16(ad[j][0], (uint16_t)e.x); sts_u16(ad[j][1], (uint16_t)e.y);
+                sts_u16(ad[j][2], (uint16_t)e.z); sts_u16(ad[j][3], (uint16_t)e.w);
+            }
+        }
+#pragma unroll 1
+        for (uint32_t i = (uint32_t)kEntCap + lane; i < n; i += 32u)            // rare: more than 448 salient weights in the pair
+            dk_patch4(tile_s + (i >= nA ? (uint32_t)dk::kTileBytes : 0u), __ldg(p.ent + (eb + i)));
+        __syncwarp();                                   // the patched tile is complete; every lane is done reading the stage
+        {
+            const uint32_t eb2 = __shfl_sync(0xffffffffu, epr, 2u * ci + 2u * kStages);
+            const uint32_t n2 = __shfl_sync(0xffffffffu, epr, 2u * ci + 2u * kStages + 2u) - eb2;
+            if (pr + (uint32_t)kStages < w_hi) { if (dk_elect()) issue(pr + (uint32_t)kStages, cs, eb2, n2); }
+        }
+
+#pragma unroll
+        for (int qi = 0; qi < 4; ++qi) {
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const uint32_t* xw = b ? X.b : X.a;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t wd = b ? (h ? sgB.y : sgB.x) : (h ? sgA.y : sgA.x);
+                    uint32_t t0, t1, t2, t3;
+                    dk_ldsm4(lm_q[qi] + (uint32_t)b * 4096u + (uint32_t)h * 2048u, t0, t1, t2, t3);
+                    const uint32_t a0 = ((wd << (4 * qi + 0)) & 0x80008000u) ^ t0;
+                    const uint32_t a1 = ((wd << (4 * qi + 1)) & 0x80008000u) ^ t1;
+                    const uint32_t a2 = ((wd << (4 * qi + 2)) & 0x80008000u) ^ t2;
+                    const uint32_t a3 = ((wd << (4 * qi + 3)) & 0x80008000u) ^ t3;
+                    dk_mma<T>(acc_d[b][h], a0, a1, a2, a3, xw[2 * qi], xw[2 * qi + 1]);
+                }
+                if (has_mid) dk_mma<T>(acc_x, kOne2, kOne2, kOne2, kOne2, xw[2 * qi], xw[2 * qi + 1]);
+            }
+        }
+
+        __syncwarp();                                   // every lane's ldmatrix reads are done: reset the entries to +1.0
+#pragma unroll
+        for (int j = 0; j < kUnitsPerLane; ++j)
+            if (lane + 32u * j < n1) {
+                sts_u16(ad[j][0], one16); sts_u16(ad[j][1], one16); sts_u16(ad[j][2], one16); sts_u16(ad[j][3], one16);
+            }
+#pragma unroll 1
+        for (uint32_t i = (uint32_t)kEntCap + lane; i < n; i += 32u)
+            dk_unpatch4(tile_s + (i >= nA ? (uint32_t)dk::kTileBytes : 0u), __ldg(p.ent + (eb + i)), one16);
+        ++ci;
+        cs ^= 1u;
+        cph ^= (cs == 0u) ? 1u : 0u;
+        __syncwarp();                                   // the resets land before the next pair's patch stores
+
+        ++kp;
+        const bool rg_end = kp == TCp;
+        if (rg_end || !more) {                          // end of this warp's part of the row group
+            fold();
+            const bool whole = rg_end && (w_lo <= rg * TCp);
+            if (whole) {                                // this warp saw the whole row group: + bias, round, store
+                store_frag(tail_red);
+                __syncwarp();
+                const int orow = (int)(rg * kRgRows + lane);
+                if (orow < p.N) {
+                    const float bv = p.bias ? p.bias[orow] : 0.f;
+#pragma unroll
+                    for (int m = 0; m < kTok; ++m)
+                        if (m0 + m < p.M) {
+                            const T v = from_f32<T>(bv + tail_red[m * kRgRows + lane]);
+                            if constexpr (kPush) {
+                                for (uint32_t d = 0; d < p.n_dst; ++d) reinterpret_cast<T*>(p.y_dst[d])[(int64_t)(m0 + m) * p.ldy + orow] = v;
+                            } else {
+                                reinterpret_cast<T*>(p.y)[(int64_t)(m0 + m) * p.ldy + orow] = v;
+                            }
+                        }
+                }
+                __syncwarp();
+                if (more) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) sts_v4(tile_s + lane * 16u + (uint32_t)i * 512u, kOne2, kOne2, kOne2, kOne2);
+                    __syncwarp();
+                }
+            } else if (rg == rg_first) {
+                store_frag(head_red);
+                if (lane == 0) s_hrg[wid] = rg;
+            } else {
+                store_frag(tail_red);
+                if (lane == 0) s_trg[wid] = rg;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[0][i] = acc[1][i] = 0.f;
+            if (rg_end) {
+                kp = 0;
+                ++rg;
+                if (more) load_levels(rg);
+            }
+        }
+    };
+    for (uint32_t pr = w_lo; pr < w_hi; pr += 2u) {
+        do_pair(pr, X0, X1);
+        if (pr + 1u < w_hi) do_pair(pr + 1u, X1, X0);
+    }
+    dk_finish<T, 1, kPush, kTrace, kWarpBytes, kTileBytes>(p, smem, s_hrg, s_trg, s_meta, c_lo, c_hi, m0, tr, w_hi - w_lo);
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------
@@ -723,27 +1052,42 @@ bool decode_supported(const Layer& L, int64_t ldx, int64_t M) {
     return true;
 }
 
-size_t decode_workspace_bytes(const Layer& L, int64_t M) {
-    if (!decode_supported(L, L.K, M)) return 0;
-    return decode_geom(L, M).ws_bytes;
+// the pair kernel's layer-side conditions (the launch adds the activation alignment): one group per row, K a multiple of
+// 128 (pairs of 64-column blocks never straddle a row group), one pass of at most 8 tokens
+static bool dk_pair_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PBL_DK_PAIR"); v = (e && *e) ? atoi(e) : 1; }
+    return v != 0;
+}
+static bool pair_layer_ok(const Layer& L, int64_t M) {
+    return dk_pair_enabled() && L.groups == 1 && (L.K & 127) == 0 && (L.tiles_c & 1) == 0 && M <= dk::kTok;
+}
+static DecodeGeom pair_geom(const Layer& L) {        // the partition in pairs of blocks: q, rem, slots in pair units
+    DecodeGeom g;
+    g.rgs = (uint32_t)(L.tiles_r * kRgPerTile);
+    g.nblocks = g.rgs * (uint32_t)L.tiles_c;
+    const uint32_t npairs = g.nblocks / 2u, tcp = (uint32_t)L.tiles_c / 2u;
+    const uint32_t want = (uint32_t)(dk_num_sms() * (dk_ctas_per_sm() < 2 ? dk_ctas_per_sm() : 2));   // shared memory: 2 CTAs per SM
+    const uint32_t cap = npairs / dk::kWarps > 0 ? npairs / dk::kWarps : 1u;
+    g.grid = cap < want ? cap : want;
+    g.q = npairs / (g.grid * dk::kWarps);
+    g.rem = npairs % (g.grid * dk::kWarps);
+    g.slots = g.q ? (tcp + 8u * g.q - 1u) / (8u * g.q) + 1u : 2u;
+    g.nt = 1u;
+    g.passes = 1u;
+    g.ws_bytes = (size_t)g.rgs * g.slots * dk::kOut * 8u;
+    return g;
 }
 
-template <typename T, int kOcc, int kNT, bool kLean, bool kPush = false>
-static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws, cudaStream_t s,
-                           const pbl_peer_push* push = nullptr) {
-    const DecodeGeom g = decode_geom(L, M);
-    const int smem = dk::kWarps * (dk::kWarpBytes + (kNT - 1) * dk::kHeadBytes);
-    static int attr_smem_dev[64] = {};   // function attributes are per device
-    int cur_dev = 0;
-    cudaGetDevice(&cur_dev);
-    if (cur_dev < 0 || cur_dev >= 64) cur_dev = 0;
-    if (attr_smem_dev[cur_dev] < smem) {
-        int rc = check_cuda(cudaFuncSetAttribute(decode_mma_kernel<T, kOcc, false, kNT, kLean, kPush>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
-                            "cudaFuncSetAttribute(decode smem)");
-        if (rc) return rc;
-        attr_smem_dev[cur_dev] = smem;
-    }
-    dk::Params p;
+size_t decode_workspace_bytes(const Layer& L, int64_t M) {
+    if (!decode_supported(L, L.K, M)) return 0;
+    size_t b = decode_geom(L, M).ws_bytes;              // whichever kernel the launch picks (it depends on the activations' alignment)
+    if (pair_layer_ok(L, M)) { const size_t pb = pair_geom(L).ws_bytes; b = pb > b ? pb : b; }
+    return b;
+}
+
+static void dk_fill_params(dk::Params& p, const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws,
+                           const DecodeGeom& g, const pbl_peer_push* push) {
     p.fsign = L.fsign; p.eptr = L.eptr; p.ent = reinterpret_cast<const uint4*>(L.ent);
     p.has_mid = (L.flags & PBL_LAYER_HAS_MID) ? 1u : 0u;
     p.affine = L.affine; p.bias = L.bias; p.x = x; p.y = y; p.ldx = ldx; p.ldy = ldy;
@@ -751,16 +1095,19 @@ static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, 
     p.M = (int)M; p.N = (int)L.N; p.K = (int)L.K;
     p.tiles_c = (uint32_t)L.tiles_c; p.groups = (uint32_t)L.groups; p.tiles_per_group = (uint32_t)L.tiles_per_group;
     p.nblocks = g.nblocks; p.rgs = g.rgs; p.slots = g.slots; p.q = g.q; p.rem = g.rem;
-    p.n_dst = 0; p.rank = 0; p.wait_prev = 0; p.flag_local = nullptr; p.sync_ctr = nullptr;
+    p.n_dst = 0; p.rank = 0; p.wait_prev = 0; p.flag_local = nullptr; p.sync_ctr = nullptr; p.trace = nullptr;
     for (int d = 0; d < PBL_MAX_PEERS; ++d) { p.y_dst[d] = nullptr; p.flag_dst[d] = nullptr; }
-    if (kPush) {
+    if (push) {
         p.n_dst = (uint32_t)push->n_ranks; p.rank = (uint32_t)push->rank; p.wait_prev = push->wait_prev ? 1u : 0u;
         p.flag_local = push->flags[push->rank]; p.sync_ctr = push->sync_ctr;
         for (int d = 0; d < push->n_ranks; ++d) { p.y_dst[d] = push->y[d]; p.flag_dst[d] = push->flags[d]; }
     }
+}
 
+template <typename K>
+static cudaError_t dk_launch(K kernel, dim3 grid, int smem, cudaStream_t s, const dk::Params& p) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(g.grid, g.passes);
+    cfg.gridDim = grid;
     cfg.blockDim = dim3(dk::kThreads);
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = s;
@@ -771,15 +1118,59 @@ static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, 
     if (pdl < 0) { const char* e = getenv("PBL_PDL"); pdl = (e && *e) ? atoi(e) : 1; }
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
+template <typename K>
+static int dk_set_smem(K kernel, int smem, int (&done)[64]) {       // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (done[dev] >= smem) return PBL_OK;
+    const int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "cudaFuncSetAttribute(decode smem)");
+    if (!rc) done[dev] = smem;
+    return rc;
+}
+
+template <typename T, bool kPush>
+static int launch_decode_pair_t(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws, cudaStream_t s,
+                                const pbl_peer_push* push = nullptr) {
+    const DecodeGeom g = pair_geom(L);
+    const int smem = dk2::kWarps * dk2::kWarpBytes;
+    dk::Params p;
+    dk_fill_params(p, L, x, ldx, y, ldy, M, ws, g, kPush ? push : nullptr);
+    cudaError_t le;
+    if (g_trace && g_trace_next < g_trace_launches && !kPush) {
+        static int done_t[64] = {};
+        if (int rc = dk_set_smem(decode_pair_kernel<T, true, false>, smem, done_t)) return rc;
+        p.trace = g_trace + (g_trace_next++) * kTraceStride;
+        le = dk_launch(decode_pair_kernel<T, true, false>, dim3(g.grid, 1), smem, s, p);
+    } else {
+        static int done[64] = {};
+        if (int rc = dk_set_smem(decode_pair_kernel<T, false, kPush>, smem, done)) return rc;
+        le = dk_launch(decode_pair_kernel<T, false, kPush>, dim3(g.grid, 1), smem, s, p);
+    }
+    count_launch();
+    return check_cuda(le, "decode (pair) launch");
+}
+
+template <typename T, int kOcc, int kNT, bool kLean, bool kPush = false>
+static int launch_decode_t(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws, cudaStream_t s,
+                           const pbl_peer_push* push = nullptr) {
+    const DecodeGeom g = decode_geom(L, M);
+    const int smem = dk::kWarps * (dk::kWarpBytes + (kNT - 1) * dk::kHeadBytes);
+    dk::Params p;
+    dk_fill_params(p, L, x, ldx, y, ldy, M, ws, g, kPush ? push : nullptr);
     cudaError_t le;
     if (g_trace && g_trace_next < g_trace_launches && kOcc == 2 && kNT == 1 && !kLean && !kPush) {
+        static int done_t[64] = {};
+        if (int rc = dk_set_smem(decode_mma_kernel<T, 2, true>, smem, done_t)) return rc;
         p.trace = g_trace + (g_trace_next++) * kTraceStride;
-        static bool tattr = false;
-        if (!tattr) { cudaFuncSetAttribute(decode_mma_kernel<T, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); tattr = true; }
-        le = cudaLaunchKernelEx(&cfg, decode_mma_kernel<T, 2, true>, p);
+        le = dk_launch(decode_mma_kernel<T, 2, true>, dim3(g.grid, g.passes), smem, s, p);
     } else {
-        p.trace = nullptr;
-        le = cudaLaunchKernelEx(&cfg, decode_mma_kernel<T, kOcc, false, kNT, kLean, kPush>, p);
+        static int done[64] = {};
+        if (int rc = dk_set_smem(decode_mma_kernel<T, kOcc, false, kNT, kLean, kPush>, smem, done)) return rc;
+        le = dk_launch(decode_mma_kernel<T, kOcc, false, kNT, kLean, kPush>, dim3(g.grid, g.passes), smem, s, p);
     }
     count_launch();
     return check_cuda(le, "decode launch");
@@ -803,7 +1194,11 @@ int launch_peer_wait(const pbl_peer_push& push, cudaStream_t s) {
 
 int launch_decode(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws, size_t ws_bytes,
                   cudaStream_t s, const pbl_peer_push* push) {
-    const DecodeGeom g = decode_geom(L, M);
+    // the lean instances: one group per row, 32-byte aligned activation rows, K a multiple of 64; with K a multiple of 128 and
+    // at most 8 tokens, the pair kernel
+    const bool aligned = L.groups == 1 && (L.K & 63) == 0 && (ldx & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 31u) == 0;
+    const bool pair = aligned && pair_layer_ok(L, M);
+    const DecodeGeom g = pair ? pair_geom(L) : decode_geom(L, M);
     void* own = nullptr;
     if (ws) {
         if (ws_bytes < g.ws_bytes) { set_error("decode workspace too small: %zu < %zu bytes", ws_bytes, g.ws_bytes); return PBL_ERR_SHAPE; }
@@ -815,8 +1210,7 @@ int launch_decode(const Layer& L, const void* x, int64_t ldx, void* y, int64_t l
         if (rc) { cudaFreeAsync(own, s); return rc; }
         ws = own;
     }
-    // the lean instance: one group per row, 32-byte aligned activation rows, K a multiple of 64 (tracing uses the generic one)
-    const bool lean = !g_trace && L.groups == 1 && (L.K & 63) == 0 && (ldx & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 31u) == 0;
+    const bool lean = !g_trace && aligned;               // (tracing the block kernel uses its generic instance)
     const bool f16 = L.dtype == PBL_F16;
     int rc;
 #define PBL_DK_LAUNCH(OCC, NT)                                                                                                 \
@@ -829,7 +1223,13 @@ int launch_decode(const Layer& L, const void* x, int64_t ldx, void* y, int64_t l
                      : launch_decode_t<__nv_bfloat16, 2, NT, true, true>(L, x, ldx, y, ldy, M, ws, s, push))                   \
               : (f16 ? launch_decode_t<__half, 2, NT, false, true>(L, x, ldx, y, ldy, M, ws, s, push)                          \
                      : launch_decode_t<__nv_bfloat16, 2, NT, false, true>(L, x, ldx, y, ldy, M, ws, s, push))
-    if (push) {
+    if (pair) {
+        rc = push ? (f16 ? launch_decode_pair_t<__half, true>(L, x, ldx, y, ldy, M, ws, s, push)
+                         : launch_decode_pair_t<__nv_bfloat16, true>(L, x, ldx, y, ldy, M, ws, s, push))
+                  : (f16 ? launch_decode_pair_t<__half, false>(L, x, ldx, y, ldy, M, ws, s)
+                         : launch_decode_pair_t<__nv_bfloat16, false>(L, x, ldx, y, ldy, M, ws, s));
+    }
+    else if (push) {
         if (g.passes != 1) { set_error("pbl_linear_forward_push: one decode pass only (M <= 16)"); rc = PBL_ERR_UNSUPPORTED; }
         else if (g.nt == 2) { PBL_DK_PUSH(2); }
         else { PBL_DK_PUSH(1); }

@@ -638,4 +638,6 @@ def test_decode_kernel_activation_alignment_paths():
         assert p.select_kernel(M) == 4
         ref = orc.linear(xv.float().cpu().numpy(), w)
         assert relmax(y, ref) <= 1e-3, off
-        assert torch.equal(y, p.forward(xv.contiguous())), off       # same bits whatever the load path
+        # the aligned call takes the pair kernel, the others the block kernel: same arithmetic, another summation order
+        yc = p.forward(xv.contiguous())
+        assert float((y.float() - yc.float()).abs().max()) <= 2.0 ** -9 * float(yc.float().abs().max()), off
