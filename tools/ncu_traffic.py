@@ -38,10 +38,10 @@ def main(prefill_rep, decode_rep):
                                    "algorithmic_bytes": 2 * 16384 * 4096 * 2 + 0.53 * 4096 * 4096,
                                    "capture": os.path.basename(prefill_rep), "duration_us_under_ncu": r["duration_us"]}
     if decode_rep and os.path.exists(decode_rep):
-        rs = [r for r in rows(decode_rep) if "decode_mma" in r["kernel"]]
+        rs = [r for r in rows(decode_rep) if "decode_" in r["kernel"]]
         if rs:
             tot = sum(r["dram_read"] + r["dram_write"] for r in rs)
-            out["decode"] = {"launch": f"decode_mma_kernel, average over the {len(rs)} captured launches (one decoder layer: q,k,v,o,gate,up,down), batch 8",
+            out["decode"] = {"launch": f"decode kernel ({rs[0]['kernel'][:40]}), average over the {len(rs)} captured launches (one decoder layer: q,k,v,o,gate,up,down), batch 8",
                              "bytes_per_launch": tot / len(rs), "per_launch": [r["dram_read"] + r["dram_write"] for r in rs],
                              "capture": os.path.basename(decode_rep)}
     json.dump(out, open(os.path.join(ROOT, "profiles", "r02_traffic.json"), "w"), indent=1)
