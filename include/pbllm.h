@@ -137,9 +137,12 @@ PBL_API int pbl_unpack(const pbl_layer* layer, void* w_out, int64_t ldw, void* s
  * quant/outlier_quantizer.py:105.  x: device [M][ldx], y: device [M][ldy] (row-major, dtype).
  * M = product of the leading dims of the reference's x[..., K].  M == 0 is a no-op.
  * fp16 / bf16 layers: calls of up to PBL_DECODE_MAX_M tokens (default 64) run the decode kernel in passes of 16 tokens;
- * larger calls first expand the weight into a transient dense scratch of 2*n_pad*k_pad bytes taken from (and returned
- * to) the device's stream-ordered memory pool on `stream` (cudaMallocAsync / cudaFreeAsync: no synchronisation,
- * CUDA-graph capturable) and run the tcgen05 GEMM over it.  fp32 layers run the CUDA-core bit-plane kernel. */
+ * larger calls first expand the weight into a dense scratch of 2*n_pad*k_pad bytes and run the tcgen05 GEMM over it.
+ * The scratch is one of two buffers the library keeps per (device, stream) and uses alternately, so that the expansion
+ * of a call can run beside the GEMM of the call before it on the same stream (grown with cudaMalloc when a larger layer
+ * arrives, kept for the life of the process; PBL_PREFILL_OVERLAP=0 turns this off).  Under stream capture, and for more
+ * than 8 streams per device, the scratch is transient: taken from and returned to the device's stream-ordered memory
+ * pool on `stream` (cudaMallocAsync / cudaFreeAsync: no synchronisation, CUDA-graph capturable).  fp32 layers run the CUDA-core bit-plane kernel. */
 PBL_API int pbl_linear_forward(const pbl_layer* layer, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M,
                        void* stream);
 
@@ -255,6 +258,11 @@ PBL_API int pbl_gptq_block(float* W1, int64_t ldw, float* err_out, int64_t lde, 
  * 1 = two-phase prefill (expansion + tcgen05 GEMM; fp16 / bf16 layers, M above PBL_DECODE_MAX_M, default 64),
  * 4 = decode kernel.  PBL_FORCE_KERNEL=0|1|4 overrides (tests). */
 PBL_API int pbl_select_kernel(const pbl_layer* layer, int64_t M);
+
+/* Which instance of the decode kernel a call with these activations would run (host-only, nothing is launched):
+ * 2 = pair kernel (one group per row, K a multiple of 128, M <= 8, x 32-byte aligned with ldx a multiple of 16 elements),
+ * 1 = general block kernel, 0 = the decode kernel does not apply (fp32 layer, M out of range).  PBL_DK_PAIR=0 disables 2. */
+PBL_API int pbl_decode_variant(const pbl_layer* layer, const void* x, int64_t ldx, int64_t M);
 
 /* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */
 PBL_API int64_t pbl_launch_count(void);

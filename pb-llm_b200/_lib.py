@@ -77,6 +77,7 @@ SYMBOLS = {
     "pbl_bireal_forward_ws": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                         C.c_void_p, C.c_size_t, C.c_void_p]),
     "pbl_select_kernel": (C.c_int, [C.c_void_p, C.c_int64]),
+    "pbl_decode_variant": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),
     "pbl_launch_count": (C.c_int64, []),
     "pbl_last_error": (C.c_char_p, []),
     "pbl_abi_version": (C.c_int, []),

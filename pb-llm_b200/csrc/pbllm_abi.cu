@@ -219,6 +219,13 @@ int pbl_select_kernel(const pbl_layer* layer, int64_t M) {
     return select_impl(L, nullptr, L.K, nullptr, L.N, M);
 }
 
+int pbl_decode_variant(const pbl_layer* layer, const void* x, int64_t ldx, int64_t M) {
+    if (!layer) { set_error("pbl_decode_variant: null layer"); return PBL_ERR_NULL; }
+    const Layer& L = *reinterpret_cast<const Layer*>(layer);
+    if (!L.fsign || M <= 0) return 0;
+    return decode_variant(L, x, ldx, M);
+}
+
 int pbl_linear_forward(const pbl_layer* layer, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M,
                        void* stream) {
     return pbl_linear_forward_ws(layer, x, ldx, y, ldy, M, nullptr, 0, stream);

@@ -75,10 +75,11 @@ int launch_stream_count(const void* w, int64_t ldw, const uint8_t* low_mask, flo
 int launch_stream_fill(const void* w, int64_t ldw, const uint8_t* low_mask, const float2* affine, int64_t N, int64_t K, int dtype,
                        const pbl_sizes& sz, int tiles_per_group, const uint32_t* eptr, uint2* fsign, uint32_t* ent, uint32_t* exc,
                        uint32_t exc_cap, uint32_t* stats, cudaStream_t s);
-int launch_stream_unpack(const Layer& L, void* out, int64_t ldw, int64_t n_rows, int64_t n_cols, cudaStream_t s);
+int launch_stream_unpack(const Layer& L, void* out, int64_t ldw, int64_t n_rows, int64_t n_cols, cudaStream_t s, bool early = false);
 int launch_gemm_twophase(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s);
 bool gemm_twophase_supported(const Layer& L, const void* x, int64_t ldx, const void* y, int64_t ldy, int64_t M);
 bool decode_supported(const Layer& L, int64_t ldx, int64_t M);
+int decode_variant(const Layer& L, const void* x, int64_t ldx, int64_t M);
 size_t decode_workspace_bytes(const Layer& L, int64_t M);
 void decode_set_trace(void* buf, size_t bytes);
 void decode_plan(int64_t N, int64_t K, int64_t M, int sms, int ctas_per_sm, uint32_t out[8]);

@@ -1192,11 +1192,21 @@ int launch_peer_wait(const pbl_peer_push& push, cudaStream_t s) {
     return check_cuda(cudaGetLastError(), "peer_wait launch");
 }
 
+// the lean instances: one group per row, 32-byte aligned activation rows, K a multiple of 64 ...
+static bool dk_aligned(const Layer& L, const void* x, int64_t ldx) {
+    return L.groups == 1 && (L.K & 63) == 0 && (ldx & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 31u) == 0;
+}
+
+// host-only (pbl_decode_variant): 2 = pair kernel, 1 = block kernel, 0 = the decode kernel does not take this call
+int decode_variant(const Layer& L, const void* x, int64_t ldx, int64_t M) {
+    if (!decode_supported(L, ldx, M)) return 0;
+    return dk_aligned(L, x, ldx) && pair_layer_ok(L, M) ? 2 : 1;
+}
+
 int launch_decode(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, void* ws, size_t ws_bytes,
                   cudaStream_t s, const pbl_peer_push* push) {
-    // the lean instances: one group per row, 32-byte aligned activation rows, K a multiple of 64; with K a multiple of 128 and
-    // at most 8 tokens, the pair kernel
-    const bool aligned = L.groups == 1 && (L.K & 63) == 0 && (ldx & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 31u) == 0;
+    // ... and with K a multiple of 128 and at most 8 tokens, the pair kernel
+    const bool aligned = dk_aligned(L, x, ldx);
     const bool pair = aligned && pair_layer_ok(L, M);
     const DecodeGeom g = pair ? pair_geom(L) : decode_geom(L, M);
     void* own = nullptr;

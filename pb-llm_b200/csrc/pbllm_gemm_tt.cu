@@ -6,6 +6,7 @@
 // for the scratch, cta_group::2 UMMA M=256 N=256, fp32 accumulators in TMEM.
 // The scratch holds exactly w_sim (bit-identical to unpack()): with x = I the kernel reproduces w_sim^T bit for bit.
 #include <cstdlib>
+#include <mutex>
 #include <type_traits>
 
 #include "pbllm_tc_ptx.cuh"
@@ -54,6 +55,9 @@ gemm_tt_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const uint32_t crank = cluster_ctarank();
     const bool leader = crank == 0;
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    // the next call's weight expansion (stream_unpack_kernel, launched with the programmatic attribute into the OTHER scratch
+    // buffer) may run beside this GEMM: it needs 17 KB of shared memory and a few percent of the issue slots we leave idle
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const uint32_t bar0 = smem_base + kOffBar;
     auto full = [&](int s) { return bar0 + 8u * s; };                        // leader only: A+B bytes of both CTAs
@@ -236,6 +240,45 @@ bool gemm_twophase_supported(const Layer& L, const void* x, int64_t ldx, const v
     return true;
 }
 
+// ---- the dense scratch -------------------------------------------------------------------------------------------
+// Two persistent buffers per (device, stream), used alternately: call i+1 expands into the buffer call i's GEMM is NOT
+// reading, so its expansion kernel can be launched early and run beside that GEMM (which it could not with one
+// stream-ordered allocation per call: the pool hands call i+1 the block call i has just freed).  Grown on demand
+// (cudaFree + cudaMalloc, synchronising, once per new maximum), kept for the life of the process.  Streams beyond the
+// table, streams under capture and allocation failures fall back to cudaMallocAsync / cudaFreeAsync without overlap.
+namespace {
+struct ScratchSlot { cudaStream_t stream; void* buf[2]; size_t bytes[2]; int flip; bool used; };
+constexpr int kScratchStreams = 8;
+ScratchSlot g_scratch[64][kScratchStreams] = {};
+std::mutex g_scratch_mu;
+bool scratch_overlap_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PBL_PREFILL_OVERLAP"); v = (e && *e) ? atoi(e) : 1; }
+    return v != 0;
+}
+void* scratch_acquire(int dev, cudaStream_t s, size_t bytes) {
+    if (!scratch_overlap_enabled() || dev < 0 || dev >= 64) return nullptr;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { (void)cudaGetLastError(); return nullptr; }
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    ScratchSlot* slot = nullptr;
+    for (int i = 0; i < kScratchStreams && !slot; ++i)
+        if (g_scratch[dev][i].used && g_scratch[dev][i].stream == s) slot = &g_scratch[dev][i];
+    for (int i = 0; i < kScratchStreams && !slot; ++i)
+        if (!g_scratch[dev][i].used) { slot = &g_scratch[dev][i]; slot->used = true; slot->stream = s; }
+    if (!slot) return nullptr;
+    const int b = slot->flip ^= 1;
+    if (slot->bytes[b] < bytes) {
+        if (slot->buf[b]) cudaFree(slot->buf[b]);          // synchronises: nothing in flight still reads it
+        slot->buf[b] = nullptr;
+        slot->bytes[b] = 0;
+        if (cudaMalloc(&slot->buf[b], bytes) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+        slot->bytes[b] = bytes;
+    }
+    return slot->buf[b];
+}
+}  // namespace
+
 int launch_gemm_twophase(const Layer& L, const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, cudaStream_t s) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled driver entry point unavailable"); return PBL_ERR_CUDA; }
@@ -257,13 +300,18 @@ int launch_gemm_twophase(const Layer& L, const void* x, int64_t ldx, void* y, in
         pool_set = true;
     }
     const size_t scratch_bytes = (size_t)L.n_pad * (size_t)L.k_pad * 2;
-    void* scratch = nullptr;
-    int rc = check_cuda(cudaMallocAsync(&scratch, scratch_bytes, s), "cudaMallocAsync(weight scratch)");
-    if (rc) return rc;
+    void* scratch = scratch_acquire(dev, s, scratch_bytes);
+    const bool pooled = scratch == nullptr;                   // transient allocation, no overlap with the kernel ahead
+    int rc = PBL_OK;
+    if (pooled) {
+        rc = check_cuda(cudaMallocAsync(&scratch, scratch_bytes, s), "cudaMallocAsync(weight scratch)");
+        if (rc) return rc;
+    }
+    auto release = [&]() { return pooled ? cudaFreeAsync(scratch, s) : cudaSuccess; };
 
     const int which = L.dtype == PBL_F16 ? 0 : 1;
-    rc = launch_stream_unpack(L, scratch, L.k_pad, L.n_pad, L.k_pad, s);      // kernel 1: the exact w_sim, padded with level values
-    if (rc) { cudaFreeAsync(scratch, s); return rc; }
+    rc = launch_stream_unpack(L, scratch, L.k_pad, L.n_pad, L.k_pad, s, !pooled);   // kernel 1: the exact w_sim, padded with level values
+    if (rc) { release(); return rc; }
 
     const int n_tiles = (int)((L.N + tt::BN - 1) / tt::BN);
     const int bm = (((M + 511) / 512) * (int64_t)n_tiles >= num_sms / 2) ? 512 : 256;
@@ -276,7 +324,7 @@ int launch_gemm_twophase(const Layer& L, const void* x, int64_t ldx, void* y, in
         const cuuint32_t box[2] = {(cuuint32_t)tt::BK, (cuuint32_t)(bm / 2)};
         CUresult cr = enc(&tmx, dt, 2, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) { cudaFreeAsync(scratch, s); set_error("cuTensorMapEncodeTiled(x) failed (%d)", (int)cr); return PBL_ERR_CUDA; }
+        if (cr != CUDA_SUCCESS) { release(); set_error("cuTensorMapEncodeTiled(x) failed (%d)", (int)cr); return PBL_ERR_CUDA; }
     }
     {
         const cuuint64_t gdim[2] = {(cuuint64_t)L.k_pad, (cuuint64_t)L.n_pad};
@@ -284,7 +332,7 @@ int launch_gemm_twophase(const Layer& L, const void* x, int64_t ldx, void* y, in
         const cuuint32_t box[2] = {(cuuint32_t)tt::BK, (cuuint32_t)tt::BNC};
         CUresult cr = enc(&tmw, dt, 2, scratch, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) { cudaFreeAsync(scratch, s); set_error("cuTensorMapEncodeTiled(w) failed (%d)", (int)cr); return PBL_ERR_CUDA; }
+        if (cr != CUDA_SUCCESS) { release(); set_error("cuTensorMapEncodeTiled(w) failed (%d)", (int)cr); return PBL_ERR_CUDA; }
     }
     GemmParams p;
     p.bias = L.bias; p.y = y; p.ldy = ldy; p.M = (int)M; p.N = (int)L.N; p.K = (int)L.K;
@@ -301,7 +349,7 @@ int launch_gemm_twophase(const Layer& L, const void* x, int64_t ldx, void* y, in
     if (!attr_done) {
         rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tt::kSmemBytes),
                         "cudaFuncSetAttribute(smem, tt)");
-        if (rc) { cudaFreeAsync(scratch, s); return rc; }
+        if (rc) { release(); return rc; }
         attr_done = true;
     }
     const int ntiles = p.m_tiles * p.n_tiles;
@@ -310,7 +358,7 @@ int launch_gemm_twophase(const Layer& L, const void* x, int64_t ldx, void* y, in
     kern<<<2 * clusters, tt::kThreads, tt::kSmemBytes, s>>>(tmx, tmw, p);
     count_launch();
     rc = check_cuda(cudaGetLastError(), "gemm_tt launch");
-    cudaError_t fe = cudaFreeAsync(scratch, s);
+    cudaError_t fe = release();
     if (!rc) rc = check_cuda(fe, "cudaFreeAsync(weight scratch)");
     return rc;
 }

@@ -313,6 +313,10 @@ __global__ void __launch_bounds__(128) stream_unpack_kernel(const uint2* __restr
             }
         }
     }
+    // Launched early (programmatic dependent launch, see launch_stream_unpack): the grid touches nothing an earlier kernel
+    // produces, but it must not COMPLETE before the kernels ahead of it have, or the kernel after it would be released
+    // too soon.  One thread waiting is enough to hold the grid open; without the launch attribute this is a no-op.
+    if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 template <typename T>
@@ -375,12 +379,25 @@ int launch_stream_fill(const void* w, int64_t ldw, const uint8_t* low_mask, cons
 
 // dense [n_rows][ldw] <- stream; n_rows / n_cols bound the rows / columns written (N, K for unpack; n_pad, k_pad for the
 // prefill scratch)
-int launch_stream_unpack(const Layer& L, void* out, int64_t ldw, int64_t n_rows, int64_t n_cols, cudaStream_t s) {
+// early: launch with the programmatic-stream-serialization attribute, so that the expansion may run beside the kernel ahead
+// of it in the stream once that kernel has executed griddepcontrol.launch_dependents (gemm_tt_kernel does, first thing).
+// Only for destinations no kernel in flight can be reading (the caller's double-buffered scratch).
+int launch_stream_unpack(const Layer& L, void* out, int64_t ldw, int64_t n_rows, int64_t n_cols, cudaStream_t s, bool early) {
     const uint32_t nblocks = (uint32_t)(L.tiles_r * kRgPerTile * L.tiles_c);
-    PBL_DISPATCH_16(L.dtype, (stream_unpack_kernel<T><<<(nblocks + 3u) / 4u, 128, 0, s>>>(L.fsign, L.eptr, L.ent, L.affine, n_rows, n_cols,
-                                                                                          (int)L.tiles_c, L.groups, L.tiles_per_group,
-                                                                                          nblocks, (T*)out, ldw)));
-    int rc = check_cuda(cudaGetLastError(), "stream_unpack launch");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((nblocks + 3u) / 4u);
+    cfg.blockDim = dim3(128);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = early ? 1 : 0;
+    cudaError_t le = cudaSuccess;
+    PBL_DISPATCH_16(L.dtype, (le = cudaLaunchKernelEx(&cfg, stream_unpack_kernel<T>, (const uint2*)L.fsign, (const uint32_t*)L.eptr,
+                                                      (const uint32_t*)L.ent, (const float2*)L.affine, n_rows, n_cols, (int)L.tiles_c,
+                                                      (int64_t)L.groups, (int)L.tiles_per_group, nblocks, (T*)out, ldw)));
+    int rc = check_cuda(le, "stream_unpack launch");
     if (rc) return rc;
     count_launch();
     if (L.n_exc) {

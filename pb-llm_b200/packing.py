@@ -371,6 +371,10 @@ class PackedLinear:
     def select_kernel(self, M: int) -> int:
         return int(_lib.load().pbl_select_kernel(self.handle, M))
 
+    def decode_variant(self, x: torch.Tensor) -> int:
+        """2 = pair kernel, 1 = block kernel, 0 = not a decode call (pbl_decode_variant) for a 2-D activation view."""
+        return int(_lib.load().pbl_decode_variant(self.handle, C.c_void_p(x.data_ptr()), x.stride(0), x.shape[0]))
+
     def unpack(self) -> torch.Tensor:
         """Dense w_sim [N,K] reconstructed bit-exactly from the packed form."""
         w = torch.empty((self.N, self.K), dtype=self.dtype, device=self.device)

@@ -61,6 +61,7 @@ def test_error_codes_without_compute():
     assert lib.pbl_forward_host_workspace(None, 4) == 0
     assert lib.pbl_linear_forward_ws(None, None, 0, None, 0, 1, None, 0, None) == -1
     assert lib.pbl_decode_workspace_bytes(None, 8) == 0
+    assert lib.pbl_decode_variant(None, None, 0, 8) == -1
     assert lib.pbl_stream_layout(4096, 4096, -1, 0, None) == -1 and lib.pbl_stream_position(0, 0, None) == -1
     ss = _lib.PblStreamSizes()
     assert lib.pbl_stream_layout(4096, 11008, -1, 0, C.byref(ss)) == 0

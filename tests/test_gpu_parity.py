@@ -224,6 +224,46 @@ def test_prefill_one_hot_activations_reproduce_w_sim_exactly():
     assert relmax(y4, w.T) <= 1e-3
 
 
+def test_prefill_back_to_back_calls_share_no_scratch():
+    """Consecutive prefill calls on one stream: the expansion of call i+1 is launched early (programmatic dependent
+    launch) into the scratch buffer call i's GEMM is NOT reading.  Layers of different sizes, no synchronisation in
+    between, every output bit-identical to the same call made alone."""
+    shapes = [(512, 256), (256, 1024), (768, 512), (512, 256)]
+    layers, xs, alone = [], [], []
+    for i, (N, K) in enumerate(shapes):
+        w, low = synth_wsim(N, K, -1, torch.float16, 300 + i)
+        layers.append(pb.PackedLinear.from_dense(t(w, torch.float16), None, t(low)))
+        xs.append(t(rounded(make_x(310 + i, (384, K)), torch.float16), torch.float16))
+    for p, x in zip(layers, xs):
+        assert p.select_kernel(x.shape[0]) == 1
+        alone.append(p.forward(x).clone())
+        torch.cuda.synchronize()
+    for rep in range(6):
+        outs = [p.forward(x) for p, x in zip(layers, xs)] + [p.forward(x) for p, x in zip(reversed(layers), reversed(xs))]
+        torch.cuda.synchronize()
+        for y, ref in zip(outs, alone + alone[::-1]):
+            assert torch.equal(y, ref), rep
+
+
+def test_prefill_inside_cuda_graph_uses_the_pool_path():
+    """Under stream capture the scratch comes from the stream-ordered pool (allocation nodes): replay reproduces the eager result."""
+    w, low = synth_wsim(512, 256, -1, torch.float16, 321)
+    p = pb.PackedLinear.from_dense(t(w, torch.float16), None, t(low))
+    x = t(rounded(make_x(322, (256, 256)), torch.float16), torch.float16)
+    ref = p.forward(x).clone()
+    out = torch.empty_like(ref)
+    side, graph = torch.cuda.Stream(), torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        p.forward(x, out=out)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            p.forward(x, out=out)
+    out.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+
+
 # ---- golden fixtures from the executed reference --------------------------------------------------
 def test_golden_cfg1_xnor_768_drop_in_ctor():
     """BASELINE config 1: OPT-125m-shaped 768x768 XnorBinaryLinear, fp32 as constructed."""
@@ -550,6 +590,60 @@ def test_decode_kernel_matches_oracle(dtype, N, K, gs, M, bias):
     assert rms_rel(y, ref) <= TOL[dtype]
     for _ in range(3):
         assert torch.equal(y, p.forward(t(x, dtype)))                # deterministic: slots are summed in CTA order
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N,K", [(32, 128), (96, 256), (320, 1152), (64, 4096), (1000, 384), (2048, 2048)])
+@pytest.mark.parametrize("M,bias", [(1, False), (3, True), (8, False)])
+def test_decode_pair_kernel_matches_oracle(dtype, N, K, M, bias):
+    """The pair kernel (K % 128 == 0, one group per row, M <= 8, aligned activations): one pair per row group (K = 128), fewer
+    pairs than warps, ragged N, row groups split across many CTAs (K = 4096), and the same call through the block kernel."""
+    w, low = synth_wsim(N, K, -1, dtype, seed=N + K + M + 1)
+    b = rounded(np.random.RandomState(5).standard_normal(N).astype(np.float32) * 0.1, dtype) if bias else None
+    x = rounded(make_x(N * 3 + M, (M, K)), dtype)
+    p = pb.PackedLinear.from_dense(t(w, dtype), None if b is None else t(b, dtype), t(low))
+    xd = t(x, dtype)
+    assert p.select_kernel(M) == 4 and p.decode_variant(xd) == 2
+    y = p.forward(xd)
+    ref = orc.linear(x, w, b)
+    assert relmax(y, ref) <= TOL[dtype], relmax(y, ref)
+    assert rms_rel(y, ref) <= TOL[dtype]
+    for _ in range(3):
+        assert torch.equal(y, p.forward(xd))                         # deterministic
+    buf = torch.zeros((M, K + 8), dtype=dtype, device=DEV)            # 16-byte aligned rows only: the block kernel
+    buf[:, 8:] = xd
+    xv = buf[:, 8:]
+    assert p.decode_variant(xv) == 1
+    yb = p.forward(xv)
+    ulp = 2.0 ** -9 if dtype == torch.float16 else 2.0 ** -6          # same arithmetic, another summation order
+    assert float((y.float() - yb.float()).abs().max()) <= ulp * float(yb.float().abs().max())
+
+
+@pytest.mark.parametrize("sal_frac", [0.0, 0.25, 0.6, 1.0])
+def test_decode_pair_kernel_dense_salient(sal_frac):
+    """No salient weights at all, and pairs with more entry units than a ring stage holds (the in-loop global loads)."""
+    N, K, M, dtype = 320, 768, 5, torch.float16
+    w, low = synth_wsim(N, K, -1, dtype, seed=int(sal_frac * 100) + 9, sal_frac=sal_frac)
+    x = rounded(make_x(23, (M, K)), dtype)
+    p = pb.PackedLinear.from_dense(t(w, dtype), None, t(low))
+    xd = t(x, dtype)
+    assert p.decode_variant(xd) == 2
+    assert relmax(p.forward(xd), orc.linear(x, w)) <= 1e-3
+
+
+def test_decode_pair_kernel_symmetric_levels():
+    """lo == -hi in every row (XnorBinaryLinear without a mean shift): the sum-of-x MMAs are skipped (no PBL_LAYER_HAS_MID)."""
+    N, K, M = 256, 512, 8
+    rs = np.random.RandomState(11)
+    alpha = (0.01 + 0.05 * rs.rand(N, 1)).astype(np.float32)
+    w = rounded(alpha * np.where(rs.rand(N, K) < 0.5, -1.0, 1.0).astype(np.float32), torch.float16)
+    w = np.where(w > 0, np.abs(w).max(1, keepdims=True), -np.abs(w).max(1, keepdims=True)).astype(np.float32)   # exactly two levels per row
+    x = rounded(make_x(31, (M, K)), torch.float16)
+    p = pb.PackedLinear.from_dense(t(w, torch.float16), None, None)
+    xd = t(x, torch.float16)
+    assert p.decode_variant(xd) == 2 and p.salient_count() == 0 and (p.flags & 1) == 0
+    assert torch.equal(p.unpack(), t(w, torch.float16))
+    assert relmax(p.forward(xd), orc.linear(x, w)) <= 1e-3
 
 
 def test_decode_kernel_workspace_sharing_and_graph():
