@@ -27,7 +27,7 @@ def main():
         for si, (name, N, K, src) in enumerate(SHAPES):
             g = torch.Generator(device=dev).manual_seed(7000 * li + si)
             w = torch.randn(N, K, device=dev, generator=g)
-            layers.append((pb.PackedLinear.from_dense((w.abs().mean(1, keepdim=True) * torch.sign(w)).half()), src))
+            layers.append((pb.PackedLinear.from_dense(w.abs().mean(1, keepdim=True) * torch.sign(w)), src))   # fp32: planes layout, as BiRealLinear packs
             del w
     M = a.batch
     xin = {"h": torch.randn(M, 4096, device=dev).half(), "a": torch.randn(M, 4096, device=dev).half(), "f": torch.randn(M, 11008, device=dev).half()}
