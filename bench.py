@@ -606,7 +606,7 @@ def main():
         b_alg = nkb / 8 + 8 * nb + Md * (2 * kb_ + 4 * nb)       # sign plane + {lo,hi} + fp16 x in + fp32 y out
         ach = b_alg / (ms_b * 1e-3) / 1e9
         xnor = {"what": "BiRealLinear forward (quant/quantizer.py:151-169) as XNOR-popcount over the packed sign plane, "
-                        "Llama-7B shapes, 224 launches per step (the kernel binarizes the activations while it stages them), CUDA graph replay",
+                        "Llama-7B shapes, 224 launches + 224 activation-binarize launches per step, CUDA graph replay",
                 "tokens_per_s": Md * world / (ms_b * 1e-3), "ms_per_step": ms_b, "batch": Md,
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                              "traffic": None, "algorithmic_bytes_per_step": b_alg, "peak_source": pk["src"]}}

@@ -127,55 +127,17 @@ struct Params {
     const uint4* planes;            // {sign0, sign1, salient0, salient1} per row (layers with zero weights) ...
     const uint2* sign_planes;       // ... or the compact sign words only (kCompact)
     const float2* affine;
-    const void* x;                  // activations [M][ldx] in their own dtype: binarized on the fly by the staging step
-    int64_t ldx;
+    const uint4* xb;
+    const int* dx;
     float* y;
     int64_t ldy;
     unsigned long long* ws;
-    int M, N, K;
-    uint32_t x_fast;                // 16-byte aligned rows and K a multiple of 64: 16-byte loads, no bounds checks
+    int M, N;
     uint32_t tiles_c, groups, tiles_per_group, rgs, slots, q, rem;
 };
 }  // namespace bsk
 
-// sign planes of one token's 64 activations of k-block k: {x>0 [0:32], x>0 [32:64], x<0 [0:32], x<0 [32:64]} -- what
-// bireal_binarize_kernel writes, computed by the lane that stages it (one launch per linear instead of two)
-template <typename TX>
-__device__ __forceinline__ uint4 br_sign_planes(const TX* __restrict__ row, uint32_t k, int K, bool fast) {
-    uint32_t pm[2] = {0u, 0u}, nm[2] = {0u, 0u};
-    const TX* ptr = row + (size_t)k * kTileCols;
-    if (fast) {
-        constexpr int kPer = 16 / (int)sizeof(TX);            // elements per 16-byte load
-#pragma unroll
-        for (int c = 0; c < kTileCols / kPer; ++c) {
-            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(ptr) + c);
-            const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-            for (int i = 0; i < kPer; ++i) {
-                float v;
-                if constexpr (sizeof(TX) == 4) {
-                    v = __uint_as_float(rw[i]);
-                } else {
-                    const uint16_t h = (uint16_t)((i & 1) ? rw[i >> 1] >> 16 : rw[i >> 1] & 0xFFFFu);
-                    v = to_f32(*reinterpret_cast<const TX*>(&h));
-                }
-                const int col = c * kPer + i;
-                pm[col >> 5] |= (v > 0.f ? 1u : 0u) << (col & 31);
-                nm[col >> 5] |= (v < 0.f ? 1u : 0u) << (col & 31);
-            }
-        }
-    } else {
-        for (int col = 0; col < kTileCols; ++col) {
-            float v = 0.f;
-            if ((int64_t)k * kTileCols + col < K) v = to_f32(ptr[col]);
-            pm[col >> 5] |= (v > 0.f ? 1u : 0u) << (col & 31);
-            nm[col >> 5] |= (v < 0.f ? 1u : 0u) << (col & 31);
-        }
-    }
-    return make_uint4(pm[0], pm[1], nm[0], nm[1]);
-}
-
-template <bool kCompact, typename TX>
+template <bool kCompact>
 __global__ void __launch_bounds__(bsk::kThreads, 4) bireal_sk_kernel(const bsk::Params p) {
     using namespace bsk;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -241,7 +203,7 @@ __global__ void __launch_bounds__(bsk::kThreads, 4) bireal_sk_kernel(const bsk::
         for (int m = 0; m < kTok; ++m) { acc[m] += af.y * (float)d1[m] + af.x * (float)d0[m]; d1[m] = d0[m] = 0; }
     };
 
-    // the activations belong to the stream's earlier kernels
+    // the activation bits come from the binarize kernel just before this one in the stream
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const uint32_t sm_tok = lane >> 2, sm_j = lane & 3u;      // staging: lane -> token, blocks j and j+4 of the chunk
@@ -262,8 +224,8 @@ __global__ void __launch_bounds__(bsk::kThreads, 4) bireal_sk_kernel(const bsk::
                 uint4 v = make_uint4(0, 0, 0, 0);
                 int dv = 0;
                 if (sm_ok && blk + i < w_hi) {
-                    v = br_sign_planes<TX>(reinterpret_cast<const TX*>(p.x) + (int64_t)(m0 + sm_tok) * p.ldx, k, p.K, p.x_fast != 0u);
-                    dv = __popc(v.x) + __popc(v.y) - __popc(v.z) - __popc(v.w);
+                    v = __ldg(p.xb + (size_t)(m0 + sm_tok) * TC + k);
+                    dv = __ldg(p.dx + (size_t)(m0 + sm_tok) * TC + k);
                 }
                 xs[i * kTok + sm_tok] = v;
                 dxs[i * kTok + sm_tok] = dv;
@@ -412,21 +374,29 @@ size_t bireal_fixup_workspace_bytes(const Layer& L, int64_t M) {
 }
 int launch_bireal(const Layer& L, const void* x, int64_t ldx, int x_dtype, float* y, int64_t ldy, int64_t M, void* workspace,
                   void* fixup_ws, size_t fixup_bytes, cudaStream_t s) {
-    if (x_dtype != PBL_F16 && x_dtype != PBL_BF16 && x_dtype != PBL_F32) { set_error("pbl_bireal_forward: bad x dtype %d", x_dtype); return PBL_ERR_DTYPE; }
+    uint4* xb = reinterpret_cast<uint4*>(workspace);
+    int* dx = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + (((size_t)M * L.tiles_c * sizeof(uint4) + 255) / 256) * 256);
+    // (xb and dx fit in bireal_scratch_bytes: M*tiles_c*20 + 256 >= the 256-rounded xb region + M*tiles_c*4)
+    const dim3 gb((unsigned)L.tiles_c, (unsigned)M);
+    switch (x_dtype) {
+        case PBL_F16: bireal_binarize_kernel<__half><<<gb, 64, 0, s>>>((const __half*)x, ldx, L.K, (int)L.tiles_c, xb, dx); break;
+        case PBL_BF16: bireal_binarize_kernel<__nv_bfloat16><<<gb, 64, 0, s>>>((const __nv_bfloat16*)x, ldx, L.K, (int)L.tiles_c, xb, dx); break;
+        case PBL_F32: bireal_binarize_kernel<float><<<gb, 64, 0, s>>>((const float*)x, ldx, L.K, (int)L.tiles_c, xb, dx); break;
+        default: set_error("pbl_bireal_forward: bad x dtype %d", x_dtype); return PBL_ERR_DTYPE;
+    }
+    int rc = check_cuda(cudaGetLastError(), "bireal binarize launch");
+    if (rc) return rc;
     if (fixup_ws && fixup_bytes >= bireal_fixup_workspace_bytes(L, M) && bireal_fixup_workspace_bytes(L, M) > 0) {
-        // a zeroed reduction workspace was given: ONE launch, the stream-K kernel balanced over all SMs binarizes the
-        // activations itself while it stages them
+        // a zeroed reduction workspace was given: stream-K kernel, balanced over all SMs
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
         uint32_t pl[8];
         decode_plan(L.N, L.K, 1, sms, 4, pl);
-        const size_t esz = x_dtype == PBL_F32 ? 4 : 2;
         bsk::Params p;
-        p.planes = L.planes; p.sign_planes = L.sign_planes; p.affine = L.affine; p.x = x; p.ldx = ldx; p.y = y; p.ldy = ldy;
+        p.planes = L.planes; p.sign_planes = L.sign_planes; p.affine = L.affine; p.xb = xb; p.dx = dx; p.y = y; p.ldy = ldy;
         p.ws = reinterpret_cast<unsigned long long*>(fixup_ws);
-        p.M = (int)M; p.N = (int)L.N; p.K = (int)L.K;
-        p.x_fast = ((reinterpret_cast<uintptr_t>(x) & 15u) == 0 && ((size_t)ldx * esz) % 16 == 0 && (L.K % kTileCols) == 0) ? 1u : 0u;
+        p.M = (int)M; p.N = (int)L.N;
         p.tiles_c = (uint32_t)L.tiles_c; p.groups = (uint32_t)L.groups; p.tiles_per_group = (uint32_t)L.tiles_per_group;
         p.rgs = pl[1]; p.slots = pl[6]; p.q = pl[4]; p.rem = pl[5];
         const int smem = bsk::kWarps * bsk::kWarpBytes;
@@ -440,28 +410,10 @@ int launch_bireal(const Layer& L, const void* x, int64_t ldx, int x_dtype, float
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t le;
-#define PBL_BSK(C)                                                                                           \
-        le = x_dtype == PBL_F16 ? cudaLaunchKernelEx(&cfg, bireal_sk_kernel<C, __half>, p)                   \
-           : x_dtype == PBL_BF16 ? cudaLaunchKernelEx(&cfg, bireal_sk_kernel<C, __nv_bfloat16>, p)           \
-                                 : cudaLaunchKernelEx(&cfg, bireal_sk_kernel<C, float>, p)
-        if (L.sign_planes) { PBL_BSK(true); } else { PBL_BSK(false); }
-#undef PBL_BSK
-        count_launch(1);
+        cudaError_t le = L.sign_planes ? cudaLaunchKernelEx(&cfg, bireal_sk_kernel<true>, p) : cudaLaunchKernelEx(&cfg, bireal_sk_kernel<false>, p);
+        count_launch(2);
         return check_cuda(le, "bireal stream-K launch");
     }
-    // no reduction workspace (or more than 64 tokens): binarize kernel + one CTA per row group
-    uint4* xb = reinterpret_cast<uint4*>(workspace);
-    int* dx = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + (((size_t)M * L.tiles_c * sizeof(uint4) + 255) / 256) * 256);
-    // (xb and dx fit in bireal_scratch_bytes: M*tiles_c*20 + 256 >= the 256-rounded xb region + M*tiles_c*4)
-    const dim3 gb((unsigned)L.tiles_c, (unsigned)M);
-    switch (x_dtype) {
-        case PBL_F16: bireal_binarize_kernel<__half><<<gb, 64, 0, s>>>((const __half*)x, ldx, L.K, (int)L.tiles_c, xb, dx); break;
-        case PBL_BF16: bireal_binarize_kernel<__nv_bfloat16><<<gb, 64, 0, s>>>((const __nv_bfloat16*)x, ldx, L.K, (int)L.tiles_c, xb, dx); break;
-        default: bireal_binarize_kernel<float><<<gb, 64, 0, s>>>((const float*)x, ldx, L.K, (int)L.tiles_c, xb, dx); break;
-    }
-    int rc = check_cuda(cudaGetLastError(), "bireal binarize launch");
-    if (rc) return rc;
     const unsigned gx = (unsigned)(L.n_pad / kRgRows);
 #define PBL_BR_LAUNCH(MT)                                                                                                      \
     do {                                                                                                                       \
