@@ -680,9 +680,12 @@ constexpr int kWarps = dk::kWarps, kThreads = dk::kThreads, kTok = dk::kTok;
 constexpr int kTileBytes = 2 * dk::kTileBytes;            // 8192: block A of the pair at 0, block B at 4096
 constexpr int kHeadBytes = dk::kHeadBytes;
 constexpr int kStages = 2;                                // pairs in flight per warp (= 4 blocks)
-constexpr int kEntCap = 112;                              // 16-byte entry units of a pair held by a ring stage (the rest: global)
-constexpr int kStageBytes = 512 + kEntCap * 16;           // 2304
-constexpr int kWarpBytes = kTileBytes + kHeadBytes + kStages * kStageBytes + 128;   // 13952: + mbarriers, padded to 128
+// 16-byte entry units of a pair held by a ring stage (the rest comes straight from global memory, a microsecond-class stall):
+// at 10 % salient weights a pair has 103 +- 5 units, so 124 covers all but one pair in 10^5 where 112 lost 3.6 % of them; it is
+// also all that two CTAs per SM leave: 2 x (8 x 14336 + 1 KB reserved + static) = 231616 of the SM's 233472 bytes
+constexpr int kEntCap = 124;
+constexpr int kStageBytes = 512 + kEntCap * 16;           // 2496
+constexpr int kWarpBytes = kTileBytes + kHeadBytes + kStages * kStageBytes + 128;   // 14336: + mbarriers, padded to 128
 constexpr int kUnitsPerLane = (kEntCap + 31) / 32;        // 4 entry units per lane and pair
 static_assert(kWarpBytes % 128 == 0, "per-warp regions must keep the tile 128-byte aligned");
 }  // namespace dk2
@@ -873,7 +876,7 @@ __global__ void __launch_bounds__(dk2::kThreads, 2) decode_pair_kernel(const dk:
             }
         }
 #pragma unroll 1
-        for (uint32_t i = (uint32_t)kEntCap + lane; i < n; i += 32u)            // rare: more than 448 salient weights in the pair
+        for (uint32_t i = (uint32_t)kEntCap + lane; i < n; i += 32u)            // rare: more than 496 salient weights in the pair
             dk_patch4(tile_s + (i >= nA ? (uint32_t)dk::kTileBytes : 0u), __ldg(p.ent + (eb + i)));
         __syncwarp();                                   // the patched tile is complete; every lane is done reading the stage
         {
