@@ -69,6 +69,8 @@ def main():
         print(json.dumps(r))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "decode_trace.json"), "w"), indent=1)
+    # raw stamps of the second decoder layer (steady state) for offline analysis: [launch][cta*8+warp][8] uint64
+    np.save(os.path.join(ROOT, "gpurun_out", "decode_trace_raw.npy"), t[7:14].copy())
 
 
 if __name__ == "__main__":
