@@ -667,9 +667,10 @@ __global__ void __launch_bounds__(dk::kThreads, kOcc) decode_mma_kernel(const dk
 // ---- the pair kernel: the common case (one group per row, K a multiple of 128, M <= 8, aligned activations) -----------
 //
 // Same layout, same arithmetic, same stream-K partition and end of kernel as decode_mma_kernel, but the unit of work is a
-// PAIR of k-adjacent blocks (32 rows x 128 columns): per-block bookkeeping is what bounded the kernel above (a warp spends
-// about 1 us per block on one serial chain wait -> patch -> barrier -> ldmatrix/MMA -> barrier -> reset -> barrier with ~250
-// issued instructions, profiles/r02_decode_ablation.md), so here
+// PAIR of k-adjacent blocks (32 rows x 128 columns).  A third of the block kernel's instructions are per-block bookkeeping
+// (ring, barriers, offsets, activation prefetch, branches for the rare cases) and its launches end on stragglers; the loop
+// itself is bound by the shared-memory pipe (ldmatrix of the tile + the 16-bit patch stores: profiles/
+// r02_decode_pair_ablation.md), which this kernel does not change.  So here
 //   * one ring stage, one mbarrier wait, one pair of bulk copies, one activation prefetch and three warp barriers serve two
 //     blocks; the warp's tile is 8 KB (block A | block B), its entries patched in one go;
 //   * the sixteen MMAs of a pair run on four independent accumulator chains (block x row half) instead of two;
