@@ -560,7 +560,7 @@ def main():
                   "ms_per_step_fused_siblings": ms_d_fused,
                   "fused_siblings_note": "pb.fuse_siblings(model): q/k/v and gate/up as one packed layer each (4 launches per decoder layer)",
                   "launch": f"CUDA graph replay of the {len(mods)} module calls",
-                  "kernel": "pbl decode pair kernel (two k-adjacent 32x64 blocks per step: sign-bit XOR +1.0 tile fragments, positioned salient entries, cp.async.bulk ring, warp-granular stream-K, mma.sync)",
+                  "kernel": ("pbl decode pair kernel (two k-adjacent 32x64 blocks per step" if Md <= 8 else "pbl decode block kernel (16 tokens per pass") + ": sign-bit XOR +1.0 tile fragments, positioned salient entries, cp.async.bulk ring, warp-granular stream-K, mma.sync)",
                   "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                                "traffic": None if tr is None else tr["bytes_per_launch"], "traffic_note": tr,
                                "algorithmic_bytes_per_launch": (b_bin + b_sal) / len(mods),
